@@ -1,0 +1,123 @@
+/*
+ * raytracer_b200.h — additive C ABI of the B200-native render path.  Nothing here exists
+ * in the reference; each entry cites the reference code whose behaviour it exposes.
+ * Plain pointers and sizes only (no torch / CUDA types in the signatures); device pointers
+ * and streams travel as void*.
+ */
+#ifndef RAYTRACER_B200_H
+#define RAYTRACER_B200_H
+
+#include "raytracer.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1u
+
+/* RtRenderOptions::flags */
+#define RT_OPT_FIXED_JITTER 0x1u  /* deterministic mode: sub-pixel offset (0.5,0.5), no jitter draws */
+#define RT_OPT_FAST_MATH    0x2u  /* relaxed-arithmetic kernel: FMA/rsqrt, statistically equal only */
+#define RT_OPT_ACCUM_IN     0x4u  /* continue from device_accum (progressive pass) */
+#define RT_OPT_ACCUM_OUT    0x8u  /* store the float4 sums back to device_accum */
+#define RT_OPT_NO_RESOLVE   0x10u /* skip the RGBA8 pack (intermediate progressive pass) */
+
+/* materials.rs:7-12 */
+#define RT_MATERIAL_DIFFUSE    0u
+#define RT_MATERIAL_METAL      1u
+#define RT_MATERIAL_DIELECTRIC 2u
+#define RT_MATERIAL_EMISSION   3u
+
+typedef struct RtRenderStats {
+  uint64_t rays;        /* World::hit calls = ray segments (common.rs:268) */
+  uint64_t samples;     /* pixel samples traced (width*height*spp of this shard) */
+  float    kernel_ms;   /* device time of the render kernel, CUDA events */
+  float    total_ms;    /* wall time of the call, copies included */
+  uint32_t launches;    /* kernels launched */
+  uint32_t grid;        /* CTAs of the persistent launch */
+  uint32_t smem_bytes;  /* primitive-list bytes staged per CTA */
+  uint32_t resident;    /* 1: primitive list lives in shared memory */
+} RtRenderStats;
+
+/* common.rs:289-294 `Options`, extended.  Zero-initialise, then set struct_size. */
+typedef struct RtRenderOptions {
+  uint32_t struct_size;        /* sizeof(RtRenderOptions) */
+  int32_t  samples_per_pixel;  /* common.rs:290 */
+  int32_t  max_ray_bounces;    /* common.rs:291 */
+  uint32_t seed;               /* 0 -> 2547549 (random.rs:9) */
+  uint32_t flags;              /* RT_OPT_* */
+  int32_t  sample_begin;       /* index of the first sample of this pass */
+  int32_t  resolve_spp;        /* divisor of the resolve; 0 -> sample_begin + samples_per_pixel */
+  int32_t  device;             /* CUDA ordinal; -1 -> current device */
+  uint32_t tile_rows;          /* row-tile height of the shard decomposition; 0 -> 16 */
+  uint32_t shard_index;        /* this call renders tiles shard_index, +shard_count, ... */
+  uint32_t shard_count;        /* 0 -> 1 */
+  uint32_t reserved;
+  RtRenderStats *stats;        /* optional out */
+} RtRenderOptions;
+
+/* Thread-local text of the last failure of any call in this library ("" if none). */
+const char *rt_last_error(void);
+uint32_t    rt_abi_version(void);
+/* Number of CUDA devices visible (0 when there is none: every render call then fails). */
+int         rt_device_count(void);
+
+/* Destructors the reference lacks (lib.rs:42-45 leaks the handle). */
+void rt_free_world(struct Rust_WorldHandle *handle);
+void rt_free_camera(struct Rust_Camera *camera);
+
+/* lib.rs:49-57 with the hard-coded Options::new(16, 8, None, true) replaced by `options`.
+ * Same framebuffer contract as render(). */
+struct Rust_CFramebuffer render_with_options(struct Rust_CFramebuffer framebuffer,
+                                             const struct Rust_WorldHandle *handle,
+                                             const RtRenderOptions *options);
+
+/* Device-resident variant for multi-GPU plumbing and benchmarks.  device_pixels: RGBA8 in
+ * device memory — the full width*height frame when shard_count <= 1, otherwise this shard's
+ * tiles packed back to back (rt_shard_pixel_count pixels).  device_accum: optional float4
+ * sums, same indexing.  stream: a cudaStream_t, or NULL for the library's own stream
+ * (then the call returns after the kernel has finished).  Returns 0 on success. */
+int rt_render_device(const struct Rust_WorldHandle *handle, const RtRenderOptions *options,
+                     size_t width, size_t height, void *device_pixels, void *device_accum,
+                     void *stream);
+size_t rt_shard_pixel_count(size_t width, size_t height, uint32_t tile_rows,
+                            uint32_t shard_index, uint32_t shard_count);
+
+/* Cameras (camera.rs:21-69).  Each replaces handle->camera, freeing the old one.
+ * Return 0 on success, non-zero where the reference asserts (camera.rs:50,:62). */
+int rt_set_camera_at(struct Rust_WorldHandle *handle, const float origin[3], float aspect_ratio);
+int rt_set_camera_vertical_fov(struct Rust_WorldHandle *handle, const float origin[3],
+                               float vertical_fov_radians, float aspect_ratio);
+int rt_set_camera_look_at(struct Rust_WorldHandle *handle, const float origin[3],
+                          const float look_at[3], const float up[3],
+                          float vertical_fov_radians, float aspect_ratio);
+/* origin, lower_left_corner, horizontal, vertical (camera.rs:8-15) as 12 floats. */
+void  rt_get_camera(const struct Rust_Camera *camera, float out12[12]);
+float rt_camera_aspect_ratio(const struct Rust_Camera *camera);   /* camera.rs:70-72 */
+
+/* Scene construction without the text parser (World::new, common.rs:233-235; the only way
+ * to reach MaterialType::Emission, which parser.rs cannot produce). */
+struct Rust_WorldHandle *rt_world_new(const float camera_origin[3], float aspect_ratio);
+int rt_world_add_sphere(struct Rust_WorldHandle *handle, const float center[3], float radius,
+                        uint32_t material, const float color[3], float param);
+int rt_world_add_triangle(struct Rust_WorldHandle *handle, const float v0[3], const float v1[3],
+                          const float v2[3], uint32_t material, const float color[3], float param);
+size_t rt_world_sphere_count(const struct Rust_WorldHandle *handle);
+size_t rt_world_triangle_count(const struct Rust_WorldHandle *handle);
+
+/* image.rs:59-81: ASCII PPM (P3), and a binary P6 variant.  Return 0 on success. */
+int rt_write_image(struct Rust_CFramebuffer framebuffer, const char *path);
+int rt_write_image_p6(struct Rust_CFramebuffer framebuffer, const char *path);
+
+/* Pinned host frame buffers: render() DMA's straight into them. */
+struct Rust_ColorU8 *rt_alloc_pixels(size_t width, size_t height);
+void                 rt_free_pixels(struct Rust_ColorU8 *pixels);
+
+/* FFMA-chain microbenchmark: measured FP32 peak of `device` in TFLOP/s (the roofline
+ * denominator of the render kernel).  Negative on failure. */
+double rt_measure_fp32_peak(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYTRACER_B200_H */

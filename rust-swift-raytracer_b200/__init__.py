@@ -1,0 +1,373 @@
+"""B200-native render path of the `raytracer` crate — Python host mirror over the C ABI.
+
+The product is `lib/libraytracer.so` (CUDA kernels for sm_100a + C++ host layer, built by
+build.py); this module is the thin ctypes binding a Python caller uses.  It mirrors the
+reference's own interface for the path, same names and argument meaning:
+
+    reference (raytracer/src/lib.rs)         here
+    ----------------------------------------------------------------------
+    load_world(source) -> WorldHandle        load_world(source) -> WorldHandle
+    render(CFramebuffer, &WorldHandle)       render(framebuffer, handle)
+    move_camera_position(camera, x, y, z)    move_camera_position(handle, x, y, z)
+    Options::new(spp, depth, ..)             Options(samples_per_pixel, max_ray_bounces, ..)
+    ray_trace(world, camera, fb, options)    ray_trace(handle, framebuffer, options)
+    image::Framebuffer / write_image         Framebuffer / write_image
+
+There is no CPU fallback anywhere: without the compiled library the import fails, and
+without a CUDA device every render call raises RenderError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "libraytracer.so"
+
+SEED_DEFAULT = 2547549            # random.rs:9
+OPT_FIXED_JITTER = 0x1
+OPT_FAST_MATH = 0x2
+OPT_ACCUM_IN = 0x4
+OPT_ACCUM_OUT = 0x8
+OPT_NO_RESOLVE = 0x10
+DIFFUSE, METAL, DIELECTRIC, EMISSION = 0, 1, 2, 3   # materials.rs:7-12
+
+
+class RenderError(RuntimeError):
+    """A call into libraytracer.so failed (text from rt_last_error())."""
+
+
+class ParseError(ValueError):
+    """load_world rejected the scene text (parser.rs:10-17)."""
+
+
+class _ColorU8(C.Structure):      # color.rs:3-10
+    _fields_ = [("r", C.c_uint8), ("g", C.c_uint8), ("b", C.c_uint8), ("a", C.c_uint8)]
+
+
+class _CFramebuffer(C.Structure):  # lib.rs:22-27
+    _fields_ = [("width", C.c_size_t), ("height", C.c_size_t), ("pixels", C.c_void_p)]
+
+
+class _WorldHandle(C.Structure):   # lib.rs:29-33
+    _fields_ = [("world", C.c_void_p), ("camera", C.c_void_p)]
+
+
+class RenderStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("kernel_ms", C.c_float),
+                ("total_ms", C.c_float), ("launches", C.c_uint32), ("grid", C.c_uint32),
+                ("smem_bytes", C.c_uint32), ("resident", C.c_uint32)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class _RenderOptions(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("samples_per_pixel", C.c_int32),
+                ("max_ray_bounces", C.c_int32), ("seed", C.c_uint32), ("flags", C.c_uint32),
+                ("sample_begin", C.c_int32), ("resolve_spp", C.c_int32), ("device", C.c_int32),
+                ("tile_rows", C.c_uint32), ("shard_index", C.c_uint32), ("shard_count", C.c_uint32),
+                ("reserved", C.c_uint32), ("stats", C.POINTER(RenderStats))]
+
+
+_lib: Optional[C.CDLL] = None
+
+# Every symbol include/raytracer.h and include/raytracer_b200.h declare.
+EXPORTED_SYMBOLS = (
+    "load_world", "render", "move_camera_position",
+    "rt_last_error", "rt_abi_version", "rt_device_count", "rt_free_world", "rt_free_camera",
+    "render_with_options", "rt_render_device", "rt_shard_pixel_count",
+    "rt_set_camera_at", "rt_set_camera_vertical_fov", "rt_set_camera_look_at", "rt_get_camera",
+    "rt_camera_aspect_ratio", "rt_world_new", "rt_world_add_sphere", "rt_world_add_triangle",
+    "rt_world_sphere_count", "rt_world_triangle_count", "rt_write_image", "rt_write_image_p6",
+    "rt_alloc_pixels", "rt_free_pixels", "rt_measure_fp32_peak",
+)
+
+
+def lib() -> C.CDLL:
+    """Load libraytracer.so (fails loudly when the extension has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(f"{LIB_PATH} is missing: run `python rust-swift-raytracer_b200/build.py` "
+                          "(there is no Python/CPU fallback for the render path)")
+    L = C.CDLL(str(LIB_PATH))
+    f3 = C.POINTER(C.c_float)
+    hp = C.POINTER(_WorldHandle)
+    L.load_world.restype = hp
+    L.load_world.argtypes = [C.c_char_p]
+    L.render.restype = _CFramebuffer
+    L.render.argtypes = [_CFramebuffer, hp]
+    L.move_camera_position.restype = C.c_void_p
+    L.move_camera_position.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
+    L.rt_last_error.restype = C.c_char_p
+    L.rt_abi_version.restype = C.c_uint32
+    L.rt_device_count.restype = C.c_int
+    L.rt_free_world.argtypes = [hp]
+    L.rt_free_world.restype = None
+    L.rt_free_camera.argtypes = [C.c_void_p]
+    L.rt_free_camera.restype = None
+    L.render_with_options.restype = _CFramebuffer
+    L.render_with_options.argtypes = [_CFramebuffer, hp, C.POINTER(_RenderOptions)]
+    L.rt_render_device.restype = C.c_int
+    L.rt_render_device.argtypes = [hp, C.POINTER(_RenderOptions), C.c_size_t, C.c_size_t, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+    L.rt_shard_pixel_count.restype = C.c_size_t
+    L.rt_shard_pixel_count.argtypes = [C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.rt_set_camera_at.restype = C.c_int
+    L.rt_set_camera_at.argtypes = [hp, f3, C.c_float]
+    L.rt_set_camera_vertical_fov.restype = C.c_int
+    L.rt_set_camera_vertical_fov.argtypes = [hp, f3, C.c_float, C.c_float]
+    L.rt_set_camera_look_at.restype = C.c_int
+    L.rt_set_camera_look_at.argtypes = [hp, f3, f3, f3, C.c_float, C.c_float]
+    L.rt_get_camera.restype = None
+    L.rt_get_camera.argtypes = [C.c_void_p, f3]
+    L.rt_camera_aspect_ratio.restype = C.c_float
+    L.rt_camera_aspect_ratio.argtypes = [C.c_void_p]
+    L.rt_world_new.restype = hp
+    L.rt_world_new.argtypes = [f3, C.c_float]
+    L.rt_world_add_sphere.restype = C.c_int
+    L.rt_world_add_sphere.argtypes = [hp, f3, C.c_float, C.c_uint32, f3, C.c_float]
+    L.rt_world_add_triangle.restype = C.c_int
+    L.rt_world_add_triangle.argtypes = [hp, f3, f3, f3, C.c_uint32, f3, C.c_float]
+    L.rt_world_sphere_count.restype = C.c_size_t
+    L.rt_world_sphere_count.argtypes = [hp]
+    L.rt_world_triangle_count.restype = C.c_size_t
+    L.rt_world_triangle_count.argtypes = [hp]
+    L.rt_write_image.restype = C.c_int
+    L.rt_write_image.argtypes = [_CFramebuffer, C.c_char_p]
+    L.rt_write_image_p6.restype = C.c_int
+    L.rt_write_image_p6.argtypes = [_CFramebuffer, C.c_char_p]
+    L.rt_alloc_pixels.restype = C.c_void_p
+    L.rt_alloc_pixels.argtypes = [C.c_size_t, C.c_size_t]
+    L.rt_free_pixels.restype = None
+    L.rt_free_pixels.argtypes = [C.c_void_p]
+    L.rt_measure_fp32_peak.restype = C.c_double
+    L.rt_measure_fp32_peak.argtypes = [C.c_int]
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().rt_last_error().decode("utf-8", "replace")
+
+
+def device_count() -> int:
+    return lib().rt_device_count()
+
+
+def _f3(v):
+    return (C.c_float * 3)(float(v[0]), float(v[1]), float(v[2]))
+
+
+@dataclass
+class Options:
+    """common.rs:289-294 `Options` (+ the additive fields of RtRenderOptions)."""
+    samples_per_pixel: int = 32          # Options::default(), common.rs:309-316
+    max_ray_bounces: int = 8
+    seed: int = SEED_DEFAULT
+    fixed_jitter: bool = False           # deterministic mode
+    fast_math: bool = False
+    sample_begin: int = 0
+    resolve_spp: int = 0
+    device: int = -1
+    tile_rows: int = 16
+    shard_index: int = 0
+    shard_count: int = 1
+    accum_in: bool = False
+    accum_out: bool = False
+    no_resolve: bool = False
+
+    def _c(self, stats: Optional[RenderStats]) -> _RenderOptions:
+        flags = ((OPT_FIXED_JITTER if self.fixed_jitter else 0) | (OPT_FAST_MATH if self.fast_math else 0) |
+                 (OPT_ACCUM_IN if self.accum_in else 0) | (OPT_ACCUM_OUT if self.accum_out else 0) |
+                 (OPT_NO_RESOLVE if self.no_resolve else 0))
+        o = _RenderOptions(C.sizeof(_RenderOptions), int(self.samples_per_pixel), int(self.max_ray_bounces),
+                           int(self.seed) & 0xFFFFFFFF, flags, int(self.sample_begin), int(self.resolve_spp),
+                           int(self.device), int(self.tile_rows), int(self.shard_index), int(self.shard_count), 0,
+                           C.pointer(stats) if stats is not None else None)
+        return o
+
+
+class Framebuffer:
+    """image.rs:9-36: row-major RGBA8, top row first.  `pinned=True` allocates the pixels with
+    rt_alloc_pixels so the frame is DMA'd straight into them."""
+
+    def __init__(self, width: int, height: int, pinned: bool = False):
+        self.width, self.height = int(width), int(height)
+        self._pinned_ptr = None
+        if pinned:
+            p = lib().rt_alloc_pixels(self.width, self.height)
+            if not p:
+                raise RenderError(last_error())
+            self._pinned_ptr = p
+            buf = (C.c_uint8 * (self.width * self.height * 4)).from_address(p)
+            self.pixels = np.frombuffer(buf, dtype=np.uint8).reshape(self.height, self.width, 4)
+            self.pixels[...] = 0
+        else:
+            self.pixels = np.zeros((self.height, self.width, 4), dtype=np.uint8)
+
+    def _c(self) -> _CFramebuffer:
+        return _CFramebuffer(self.width, self.height, self.pixels.ctypes.data)
+
+    def __del__(self):
+        if getattr(self, "_pinned_ptr", None):
+            self.pixels = None
+            lib().rt_free_pixels(self._pinned_ptr)
+            self._pinned_ptr = None
+
+
+class WorldHandle:
+    """lib.rs:29-33: owns the Rust_WorldHandle* returned by load_world / rt_world_new."""
+
+    def __init__(self, ptr):
+        self._ptr = ptr
+
+    @property
+    def ptr(self):
+        if not self._ptr:
+            raise RenderError("world handle already freed")
+        return self._ptr
+
+    def free(self):
+        if self._ptr:
+            lib().rt_free_world(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    # ---- scene ----
+    @property
+    def n_spheres(self) -> int:
+        return lib().rt_world_sphere_count(self.ptr)
+
+    @property
+    def n_triangles(self) -> int:
+        return lib().rt_world_triangle_count(self.ptr)
+
+    def add_sphere(self, center, radius, material=DIFFUSE, color=(1.0, 1.0, 1.0), param=0.0):
+        if lib().rt_world_add_sphere(self.ptr, _f3(center), float(radius), int(material), _f3(color), float(param)):
+            raise RenderError(last_error())
+
+    def add_triangle(self, v0, v1, v2, material=DIFFUSE, color=(1.0, 1.0, 1.0), param=0.0):
+        if lib().rt_world_add_triangle(self.ptr, _f3(v0), _f3(v1), _f3(v2), int(material), _f3(color), float(param)):
+            raise RenderError(last_error())
+
+    # ---- camera (camera.rs:21-72) ----
+    def camera_floats(self) -> np.ndarray:
+        out = (C.c_float * 12)()
+        lib().rt_get_camera(self.ptr.contents.camera, out)
+        return np.array(out, dtype=np.float32)
+
+    def aspect_ratio(self) -> float:
+        return lib().rt_camera_aspect_ratio(self.ptr.contents.camera)
+
+    def set_camera_at(self, origin, aspect):
+        if lib().rt_set_camera_at(self.ptr, _f3(origin), float(aspect)):
+            raise RenderError(last_error())
+
+    def set_camera_vertical_fov(self, origin, vfov, aspect):
+        if lib().rt_set_camera_vertical_fov(self.ptr, _f3(origin), float(vfov), float(aspect)):
+            raise RenderError(last_error())
+
+    def set_camera_look_at(self, origin, look_at, up, vfov, aspect):
+        if lib().rt_set_camera_look_at(self.ptr, _f3(origin), _f3(look_at), _f3(up), float(vfov), float(aspect)):
+            raise RenderError(last_error())
+
+
+def load_world(source) -> WorldHandle:
+    """lib.rs:37-46.  Raises ParseError where the reference panics."""
+    if isinstance(source, str):
+        source = source.encode("utf-8")
+    p = lib().load_world(source)
+    if not p:
+        raise ParseError(last_error())
+    return WorldHandle(p)
+
+
+def world_new(camera_origin=(0.0, 0.0, 0.0), aspect_ratio=1.77778) -> WorldHandle:
+    """World::new (common.rs:233-235) + Camera::new_at, without the text parser."""
+    return WorldHandle(lib().rt_world_new(_f3(camera_origin), float(aspect_ratio)))
+
+
+def move_camera_position(handle: WorldHandle, x: float, y: float, z: float) -> None:
+    """lib.rs:60-63 used the way GameView.swift:200-216 uses it:
+    handle.camera = move_camera_position(handle.camera, x, y, z)."""
+    h = handle.ptr
+    new = lib().move_camera_position(h.contents.camera, float(x), float(y), float(z))
+    if not new:
+        raise RenderError(last_error())
+    h.contents.camera = new
+
+
+def render(framebuffer: Framebuffer, handle: WorldHandle) -> Framebuffer:
+    """lib.rs:49-57: 16 spp, depth 8, into framebuffer.pixels."""
+    lib().render(framebuffer._c(), handle.ptr)
+    err = last_error()
+    if err:
+        raise RenderError(err)
+    return framebuffer
+
+
+def render_with_options(framebuffer: Framebuffer, handle: WorldHandle, options: Options,
+                        stats: Optional[RenderStats] = None) -> Framebuffer:
+    o = options._c(stats)
+    lib().render_with_options(framebuffer._c(), handle.ptr, C.byref(o))
+    err = last_error()
+    if err:
+        raise RenderError(err)
+    return framebuffer
+
+
+def ray_trace(handle: WorldHandle, framebuffer: Framebuffer, options: Options,
+              stats: Optional[RenderStats] = None) -> Framebuffer:
+    """common.rs:320-361 (world + camera travel together in the handle, as in lib.rs:53-54)."""
+    return render_with_options(framebuffer, handle, options, stats)
+
+
+def render_device(handle: WorldHandle, options: Options, width: int, height: int, device_pixels: int,
+                  device_accum: int = 0, stream: int = 0, stats: Optional[RenderStats] = None) -> None:
+    """rt_render_device: device_pixels / device_accum / stream are raw addresses
+    (e.g. torch.Tensor.data_ptr(), torch.cuda.Stream.cuda_stream)."""
+    o = options._c(stats)
+    rc = lib().rt_render_device(handle.ptr, C.byref(o), int(width), int(height),
+                                C.c_void_p(device_pixels or None), C.c_void_p(device_accum or None),
+                                C.c_void_p(stream or None))
+    if rc:
+        raise RenderError(last_error())
+
+
+def shard_pixel_count(width: int, height: int, tile_rows: int, shard_index: int, shard_count: int) -> int:
+    return lib().rt_shard_pixel_count(width, height, tile_rows, shard_index, shard_count)
+
+
+def write_image(framebuffer: Framebuffer, path: str, binary: bool = False) -> None:
+    """image.rs:59-81 (ASCII P3); binary=True writes P6."""
+    f = lib().rt_write_image_p6 if binary else lib().rt_write_image
+    if f(framebuffer._c(), str(path).encode()):
+        raise OSError(last_error())
+
+
+def measure_fp32_peak(device: int = -1) -> float:
+    v = lib().rt_measure_fp32_peak(device)
+    if v < 0:
+        raise RenderError(last_error())
+    return v
+
+
+# ---- shard geometry shared by the multi-GPU plumbing (tile t belongs to rank t % N) ----
+
+def shard_tiles(height: int, tile_rows: int, shard_index: int, shard_count: int):
+    """Image-row ranges [(r0, r1), ...] of the tiles shard `shard_index` renders, in the order
+    they are packed in its compact buffer."""
+    n_tiles = (height + tile_rows - 1) // tile_rows
+    return [(t * tile_rows, min((t + 1) * tile_rows, height)) for t in range(shard_index, n_tiles, shard_count)]

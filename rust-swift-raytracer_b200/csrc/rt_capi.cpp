@@ -1,0 +1,267 @@
+// rt_capi.cpp — the C ABI (include/raytracer.h + include/raytracer_b200.h) over the C++
+// host layer.  No exception crosses this boundary: failures set a thread-local error string.
+#include "../../include/raytracer_b200.h"
+#include "rt_host.hpp"
+
+#include <cstring>
+#include <exception>
+#include <stdexcept>
+#include <string>
+
+// The opaque ABI types are the C++ host objects.
+struct Rust_World  { std::unique_ptr<rt::World> world; };
+struct Rust_Camera { rt::Camera camera; };
+
+namespace {
+
+thread_local std::string g_error;
+
+void set_error(const std::string& s) { g_error = s; }
+void clear_error() { g_error.clear(); }
+
+rt::Options to_options(const RtRenderOptions* o)
+{
+    rt::Options r;
+    if (!o) { r.samples_per_pixel = 16; r.max_ray_bounces = 8; return r; }   // lib.rs:51
+    RtRenderOptions c;
+    std::memset(&c, 0, sizeof c);
+    std::memcpy(&c, o, o->struct_size && o->struct_size < sizeof c ? o->struct_size : sizeof c);
+    r.samples_per_pixel = c.samples_per_pixel;
+    r.max_ray_bounces   = c.max_ray_bounces;
+    r.seed              = c.seed ? c.seed : 2547549u;
+    r.fixed_jitter      = (c.flags & RT_OPT_FIXED_JITTER) != 0;
+    r.fast_math         = (c.flags & RT_OPT_FAST_MATH) != 0;
+    r.accum_in          = (c.flags & RT_OPT_ACCUM_IN) != 0;
+    r.accum_out         = (c.flags & RT_OPT_ACCUM_OUT) != 0;
+    r.no_resolve        = (c.flags & RT_OPT_NO_RESOLVE) != 0;
+    r.sample_begin      = c.sample_begin;
+    r.resolve_spp       = c.resolve_spp;
+    r.device            = c.device;
+    r.tile_rows         = c.tile_rows ? c.tile_rows : 16u;
+    r.shard_index       = c.shard_index;
+    r.shard_count       = c.shard_count ? c.shard_count : 1u;
+    return r;
+}
+
+void export_stats(const rt::RenderStats& s, RtRenderStats* out)
+{
+    out->rays = s.rays; out->samples = s.samples; out->kernel_ms = s.kernel_ms; out->total_ms = s.total_ms;
+    out->launches = s.launches; out->grid = s.grid; out->smem_bytes = s.smem_bytes; out->resident = s.resident;
+}
+
+template <class F>
+int guarded(F&& f)
+{
+    clear_error();
+    try { f(); return 0; }
+    catch (const std::exception& e) { set_error(e.what()); }
+    catch (...) { set_error("unknown error"); }
+    return 1;
+}
+
+rt::Material make_material(uint32_t type, const float color[3], float param)
+{
+    rt::Material m;
+    m.type = (RtMaterialType)type;
+    m.r = color ? color[0] : 1.f; m.g = color ? color[1] : 1.f; m.b = color ? color[2] : 1.f;
+    m.param = param;
+    return m;
+}
+
+void replace_camera(Rust_WorldHandle* h, const rt::Camera& c)
+{
+    delete h->camera;
+    h->camera = new Rust_Camera{c};
+}
+
+}   // namespace
+
+extern "C" {
+
+const char* rt_last_error(void) { return g_error.c_str(); }
+uint32_t    rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+int         rt_device_count(void) { return rt::device_count(); }
+
+Rust_WorldHandle* load_world(const char* source)
+{
+    clear_error();
+    if (!source) { set_error("load_world: source is NULL"); return nullptr; }
+    try {
+        rt::ParseResult r = rt::parse_input(source, std::strlen(source));
+        if (r.error != rt::ParseError::Ok) {
+            set_error(std::string("load_world: ParseError: ") + rt::parse_error_name(r.error));
+            return nullptr;
+        }
+        auto* h   = new Rust_WorldHandle;
+        h->world  = new Rust_World{std::move(r.world)};
+        h->camera = new Rust_Camera{r.camera};
+        return h;
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return nullptr;
+    }
+}
+
+Rust_Camera* move_camera_position(Rust_Camera* camera, float x, float y, float z)
+{
+    clear_error();
+    if (!camera) { set_error("move_camera_position: camera is NULL"); return nullptr; }
+    auto* moved = new Rust_Camera{camera->camera.moved(x, y, z)};
+    delete camera;   // Box<Camera> taken by value (lib.rs:60)
+    return moved;
+}
+
+Rust_CFramebuffer render_with_options(Rust_CFramebuffer fb, const Rust_WorldHandle* handle,
+                                      const RtRenderOptions* options)
+{
+    guarded([&] {
+        if (!handle || !handle->world || !handle->camera) throw std::runtime_error("render: NULL world handle");
+        if (!fb.pixels) throw std::runtime_error("render: framebuffer.pixels is NULL");
+        rt::Options     o = to_options(options);
+        rt::RenderStats st;
+        RtRenderStats*  out_stats = (options && options->struct_size >= sizeof(RtRenderOptions)) ? options->stats : nullptr;
+        if (out_stats) o.stats = &st;
+        rt::ray_trace_into(*handle->world->world, handle->camera->camera, fb.width, fb.height, o,
+                           reinterpret_cast<rt::ColorU8*>(fb.pixels), nullptr, nullptr, nullptr);
+        if (out_stats) export_stats(st, out_stats);
+    });
+    return fb;
+}
+
+Rust_CFramebuffer render(Rust_CFramebuffer fb, const Rust_WorldHandle* handle)
+{
+    return render_with_options(fb, handle, nullptr);   // Options::new(16, 8, None, true), lib.rs:51
+}
+
+int rt_render_device(const Rust_WorldHandle* handle, const RtRenderOptions* options, size_t width, size_t height,
+                     void* device_pixels, void* device_accum, void* stream)
+{
+    return guarded([&] {
+        if (!handle || !handle->world || !handle->camera) throw std::runtime_error("rt_render_device: NULL world handle");
+        rt::Options     o = to_options(options);
+        rt::RenderStats st;
+        RtRenderStats*  out_stats = (options && options->struct_size >= sizeof(RtRenderOptions)) ? options->stats : nullptr;
+        if (out_stats) o.stats = &st;
+        if (!device_pixels && !o.no_resolve) throw std::runtime_error("rt_render_device: device_pixels is NULL");
+        rt::ray_trace_into(*handle->world->world, handle->camera->camera, width, height, o, nullptr, device_pixels,
+                           device_accum, stream);
+        if (out_stats) export_stats(st, out_stats);
+    });
+}
+
+size_t rt_shard_pixel_count(size_t width, size_t height, uint32_t tile_rows, uint32_t shard_index, uint32_t shard_count)
+{
+    if (!tile_rows) tile_rows = 16;
+    if (!shard_count) shard_count = 1;
+    if (shard_count == 1) return width * height;
+    return (size_t)rt::shard_tile_count((uint32_t)height, tile_rows, shard_index, shard_count) * tile_rows * width;
+}
+
+void rt_free_world(Rust_WorldHandle* h)
+{
+    if (!h) return;
+    delete h->world;
+    delete h->camera;
+    delete h;
+}
+void rt_free_camera(Rust_Camera* c) { delete c; }
+
+int rt_set_camera_at(Rust_WorldHandle* h, const float origin[3], float aspect)
+{
+    return guarded([&] {
+        if (!h) throw std::runtime_error("NULL world handle");
+        replace_camera(h, rt::Camera::new_at(RtVec3{origin[0], origin[1], origin[2]}, aspect));
+    });
+}
+int rt_set_camera_vertical_fov(Rust_WorldHandle* h, const float origin[3], float vfov, float aspect)
+{
+    return guarded([&] {
+        if (!h) throw std::runtime_error("NULL world handle");
+        replace_camera(h, rt::Camera::new_with_vertical_fov(RtVec3{origin[0], origin[1], origin[2]}, vfov, aspect));
+    });
+}
+int rt_set_camera_look_at(Rust_WorldHandle* h, const float origin[3], const float look_at[3], const float up[3],
+                          float vfov, float aspect)
+{
+    return guarded([&] {
+        if (!h) throw std::runtime_error("NULL world handle");
+        rt::Camera  c;
+        std::string err;
+        if (!rt::Camera::new_look_at(RtVec3{origin[0], origin[1], origin[2]}, RtVec3{look_at[0], look_at[1], look_at[2]},
+                                     RtVec3{up[0], up[1], up[2]}, vfov, aspect, &c, &err))
+            throw std::runtime_error(err);
+        replace_camera(h, c);
+    });
+}
+void rt_get_camera(const Rust_Camera* camera, float out12[12])
+{
+    if (!camera) return;
+    std::memcpy(out12, &camera->camera.d, 12 * sizeof(float));
+}
+float rt_camera_aspect_ratio(const Rust_Camera* camera) { return camera ? camera->camera.aspect_ratio() : 0.f; }
+
+Rust_WorldHandle* rt_world_new(const float origin[3], float aspect)
+{
+    clear_error();
+    auto* h   = new Rust_WorldHandle;
+    h->world  = new Rust_World{rt::World::make({}, {})};
+    h->camera = new Rust_Camera{rt::Camera::new_at(origin ? RtVec3{origin[0], origin[1], origin[2]} : RtVec3{0, 0, 0}, aspect)};
+    return h;
+}
+int rt_world_add_sphere(Rust_WorldHandle* h, const float center[3], float radius, uint32_t material,
+                        const float color[3], float param)
+{
+    return guarded([&] {
+        if (!h || !h->world) throw std::runtime_error("NULL world handle");
+        if (material > RT_MATERIAL_EMISSION) throw std::runtime_error("unknown material type");
+        h->world->world->spheres.push_back(rt::Sphere{RtVec3{center[0], center[1], center[2]}, radius,
+                                                      make_material(material, color, param)});
+        h->world->world->invalidate_device();
+    });
+}
+int rt_world_add_triangle(Rust_WorldHandle* h, const float v0[3], const float v1[3], const float v2[3],
+                          uint32_t material, const float color[3], float param)
+{
+    return guarded([&] {
+        if (!h || !h->world) throw std::runtime_error("NULL world handle");
+        if (material > RT_MATERIAL_EMISSION) throw std::runtime_error("unknown material type");
+        h->world->world->triangles.push_back(rt::Triangle::make(RtVec3{v0[0], v0[1], v0[2]}, RtVec3{v1[0], v1[1], v1[2]},
+                                                                RtVec3{v2[0], v2[1], v2[2]},
+                                                                make_material(material, color, param)));
+        h->world->world->invalidate_device();
+    });
+}
+size_t rt_world_sphere_count(const Rust_WorldHandle* h) { return (h && h->world) ? h->world->world->spheres.size() : 0; }
+size_t rt_world_triangle_count(const Rust_WorldHandle* h) { return (h && h->world) ? h->world->world->triangles.size() : 0; }
+
+static int write_any(Rust_CFramebuffer fb, const char* path, bool p6)
+{
+    return guarded([&] {
+        if (!fb.pixels) throw std::runtime_error("framebuffer.pixels is NULL");
+        rt::Framebuffer f;
+        f.width = fb.width; f.height = fb.height;
+        f.pixels.resize(fb.width * fb.height);
+        std::memcpy(f.pixels.data(), fb.pixels, fb.width * fb.height * 4);
+        if (!(p6 ? rt::write_image_p6(f, path) : rt::write_image(f, path))) throw std::runtime_error("cannot write image");
+    });
+}
+int rt_write_image(Rust_CFramebuffer fb, const char* path) { return write_any(fb, path, false); }
+int rt_write_image_p6(Rust_CFramebuffer fb, const char* path) { return write_any(fb, path, true); }
+
+Rust_ColorU8* rt_alloc_pixels(size_t width, size_t height)
+{
+    clear_error();
+    void* p = rt::alloc_pinned(width * height * 4);
+    if (!p) set_error("rt_alloc_pixels: pinned allocation failed (no CUDA device?)");
+    return static_cast<Rust_ColorU8*>(p);
+}
+void rt_free_pixels(Rust_ColorU8* pixels) { rt::free_pinned(pixels); }
+
+double rt_measure_fp32_peak(int device)
+{
+    double v = -1.0;
+    guarded([&] { v = rt::measure_fp32_peak_tflops(device, nullptr); });
+    return v;
+}
+
+}   // extern "C"

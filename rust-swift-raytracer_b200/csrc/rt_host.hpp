@@ -1,0 +1,179 @@
+// rt_host.hpp — C++ host layer above the CUDA kernels.
+//
+// The reference's host side is Rust; this image has no Rust toolchain, so the host layer is
+// C++ that mirrors the crate's public API for the render path name for name:
+//
+//   reference (raytracer/src/...)                      here (namespace rt)
+//   ---------------------------------------------------------------------------------
+//   materials.rs:7-12   MaterialType                   Material
+//   common.rs:54-58     Sphere                         Sphere
+//   common.rs:101-123   Triangle, Triangle::new        Triangle, Triangle::make
+//   common.rs:227-235   World, World::new              World, World::make
+//   camera.rs:8-72      Camera, new_at, new_with_vertical_fov, new_look_at, aspect_ratio
+//   common.rs:289-317   Options                        Options (+ seed / flags / sharding)
+//   image.rs:9-36       Framebuffer                    Framebuffer
+//   common.rs:320-361   ray_trace                      ray_trace           (runs on the GPU)
+//   parser.rs:336-382   parse_input                    parse_input
+//   image.rs:59-81      write_image                    write_image
+//
+// There is no CPU implementation of ray_trace in this library: without a CUDA device every
+// render call fails with an error (never a silent fallback).
+#pragma once
+#include "rt_types.h"
+
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace rt {
+
+// materials.rs:7-12
+struct Material {
+    RtMaterialType type  = RT_MAT_DIFFUSE;
+    float          r = 0.f, g = 0.f, b = 0.f;   // Color (alpha == 1, color.rs:21-23)
+    float          param = 0.f;                 // Metal: fuzz, Dielectric: ir
+    static Material Diffuse(float r, float g, float b) { return {RT_MAT_DIFFUSE, r, g, b, 0.f}; }
+    static Material Metal(float r, float g, float b, float fuzz) { return {RT_MAT_METAL, r, g, b, fuzz}; }
+    static Material Dielectric(float ir) { return {RT_MAT_DIELECTRIC, 1.f, 1.f, 1.f, ir}; }
+    static Material Emission(float r, float g, float b) { return {RT_MAT_EMISSION, r, g, b, 0.f}; }
+};
+
+// common.rs:54-58
+struct Sphere {
+    RtVec3   center;
+    float    radius;
+    Material material;
+};
+
+// common.rs:101-107
+struct Triangle {
+    RtVec3   v0, v1, v2;
+    RtVec3   normal;     // normalize((v1-v0) x (v2-v0)), common.rs:116-123
+    Material material;
+    static Triangle make(RtVec3 v0, RtVec3 v1, RtVec3 v2, const Material& m);
+};
+
+// camera.rs:8-15
+struct Camera {
+    RtCameraData d;
+    static Camera new_at(RtVec3 origin, float aspect_ratio);                              // :21-33
+    static Camera new_with_vertical_fov(RtVec3 origin, float vfov_radians, float aspect); // :34-48
+    // :49-69.  Returns false (and sets *error) where the reference asserts.
+    static bool new_look_at(RtVec3 origin, RtVec3 look_at, RtVec3 up, float vfov_radians, float aspect,
+                            Camera* out, std::string* error);
+    float  aspect_ratio() const { return d.horizontal.x / d.vertical.y; }                 // :70-72
+    RtVec3 position() const { return d.origin; }                                          // :91-93
+    Camera moved(float x, float y, float z) const;                                        // lib.rs:60-63
+};
+
+// image.rs:9-36 + color.rs:3-10
+struct ColorU8 { uint8_t r, g, b, a; };
+struct Framebuffer {
+    size_t               width = 0, height = 0;
+    std::vector<ColorU8> pixels;   // row-major, top row first
+    Framebuffer() = default;
+    Framebuffer(size_t w, size_t h) : width(w), height(h), pixels(w * h, ColorU8{0, 0, 0, 0}) {}
+};
+
+// Per-render statistics (additive; the reference reports nothing).
+struct RenderStats {
+    uint64_t rays       = 0;     // World::hit calls (ray segments)
+    uint64_t samples    = 0;     // pixel samples traced
+    float    kernel_ms  = 0.f;   // device time of the render kernel(s), CUDA events
+    float    total_ms   = 0.f;   // wall time of the call including copies
+    uint32_t launches   = 0;     // kernels launched by this call
+    uint32_t grid       = 0;
+    uint32_t smem_bytes = 0;
+    uint32_t resident   = 0;     // 1: primitive list staged in shared memory
+};
+
+// common.rs:289-294, extended.  The reference fields keep their names.
+struct Options {
+    int32_t  samples_per_pixel = 32;        // Options::default(), common.rs:309-316
+    int32_t  max_ray_bounces   = 8;
+    bool     positive_is_up    = true;      // stored, never read (as in the reference)
+    // ---- additive ----
+    uint32_t seed           = 2547549u;     // random.rs:9
+    bool     fixed_jitter   = false;        // deterministic mode: sub-pixel offset (0.5, 0.5)
+    bool     fast_math      = false;        // relaxed-arithmetic kernel (not bit-exact)
+    int32_t  sample_begin   = 0;            // first sample index of this pass
+    int32_t  resolve_spp    = 0;            // 0: sample_begin + samples_per_pixel
+    int32_t  device         = -1;           // CUDA device ordinal, -1: current device
+    uint32_t tile_rows      = 16;           // row-tile height of the shard decomposition
+    uint32_t shard_index    = 0;            // this shard renders tiles shard_index, +shard_count, ...
+    uint32_t shard_count    = 1;
+    bool     accum_in       = false;        // continue from the float4 accumulator (progressive)
+    bool     accum_out      = false;        // write the float4 accumulator back
+    bool     no_resolve     = false;        // skip the RGBA8 pack (intermediate pass)
+    RenderStats* stats      = nullptr;
+};
+
+struct DeviceScene;   // per-device packed scene (defined in rt_device.cu)
+
+// common.rs:227-235.  Holds the primitives in list order and the lazily built device copies.
+struct World {
+    std::vector<Sphere>   spheres;
+    std::vector<Triangle> triangles;     // the single Mesh of lib.rs:41 / main.rs:58-79
+    World();
+    ~World();
+    World(const World&)            = delete;
+    World& operator=(const World&) = delete;
+    static std::unique_ptr<World> make(std::vector<Sphere> spheres, std::vector<Triangle> triangles);
+    void invalidate_device();            // call after editing spheres/triangles
+    // packed host copy of the scene blob (rt_types.h layout), built on demand
+    struct Packed {
+        std::vector<unsigned char> blob;
+        size_t off_sph = 0, off_tri_plane = 0, off_tri_v = 0, off_mat = 0, off_sph_r = 0, off_mat_type = 0;
+        uint32_t n_sph = 0, n_tri = 0;
+        RtSceneView view(const unsigned char* base) const;
+    };
+    const Packed& packed() const;
+    // internal
+    mutable std::unique_ptr<Packed>                   packed_;
+    mutable std::vector<std::unique_ptr<DeviceScene>> device_;
+};
+
+// parser.rs:10-17
+enum class ParseError { Ok = 0, CouldntOpenFile, MissingCamera, WrongSyntax, DidntStartWith, NotAI32, NotAF32, InvalidUtf8 };
+const char* parse_error_name(ParseError e);
+
+struct ParseResult {
+    ParseError             error = ParseError::Ok;
+    Camera                 camera{};
+    std::unique_ptr<World> world;
+};
+// parser.rs:336-382 (source need not be NUL-terminated here)
+ParseResult parse_input(const char* source, size_t length);
+
+// common.rs:320-361 on the GPU.  Renders into framebuffer.pixels and returns it.
+// Throws std::runtime_error on any CUDA failure (no CPU fallback exists).
+Framebuffer ray_trace(const World& world, const Camera& camera, Framebuffer framebuffer, Options& options);
+
+// The same render with explicit destinations:
+//  host_pixels   : width*height RGBA8 in host memory (pageable or pinned), or nullptr
+//  device_pixels : RGBA8 in device memory (full frame, or this shard's tiles packed when
+//                  shard_count > 1), or nullptr to use an internal buffer
+//  device_accum  : optional float4 accumulator in device memory (progressive passes)
+//  stream        : cudaStream_t (nullptr: the library's own stream, call is synchronous)
+void ray_trace_into(const World& world, const Camera& camera, size_t width, size_t height,
+                    const Options& options, ColorU8* host_pixels, void* device_pixels,
+                    void* device_accum, void* stream);
+
+// Number of rows / pixels shard `index` of `count` owns for an image of `height` rows.
+uint32_t shard_tile_count(uint32_t height, uint32_t tile_rows, uint32_t index, uint32_t count);
+
+// image.rs:59-81 (ASCII P3) and a binary P6 variant.  Return false on I/O failure.
+bool write_image(const Framebuffer& fb, const char* path);
+bool write_image_p6(const Framebuffer& fb, const char* path);
+
+// Device utilities
+int    device_count();
+// FFMA-chain microbenchmark: measured FP32 peak of `device` in TFLOP/s (FMA = 2 flops).
+double measure_fp32_peak_tflops(int device, float* sm_clock_mhz_out);
+// Pinned host allocations for callers that want the frame DMA'd straight into their buffer.
+void* alloc_pinned(size_t bytes);
+void  free_pinned(void* p);
+
+}   // namespace rt

@@ -1,0 +1,264 @@
+// rt_kernels.cuh — the render kernel (sm_100a), shared by the exact and the fast
+// translation units.
+//
+// One persistent launch per frame (or per progressive pass) replaces the reference's
+// row -> column -> sample -> bounce loop nest (common.rs:320-361):
+//
+//   * grid = (#SMs x resident CTAs per SM) CTAs of RT_BLOCK threads; every warp pulls work
+//     from one global counter in slabs of RT_RESERVE pixel slots, so the frame is balanced
+//     dynamically and no CTA wave tail exists.
+//   * one LANE owns one pixel at a time and adds that pixel's samples in order (float
+//     addition is not associative — this is what keeps the sums bit-identical to
+//     common.rs:338-340).  A lane whose path ends starts its next sample in the very next
+//     iteration, and a lane whose pixel is finished takes the next pixel slot (warp-level
+//     ballot/popc compaction of the slab) — no lane ever waits for its neighbours' longer
+//     paths.  Each loop iteration traces exactly one ray segment per live lane.
+//   * the primitive list ({c, r*r} per sphere, {n, n.v0} per triangle — 16 B each) is staged
+//     once per CTA into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier);
+//     every warp then reads it with broadcast LDS.128.  Scenes too large for shared memory
+//     fall back to the same loop over global memory (L1/L2 broadcast loads).
+//   * accumulate + sqrt-gamma + RGBA8 pack + vertical flip are fused at the end of each
+//     pixel: one 32-bit store per pixel, no intermediate framebuffer pass.
+//   * the pixel order inside a slab is 8x4 tiles, so a warp's primary rays are coherent.
+#pragma once
+#include "rt_trace.cuh"
+
+#include <cuda_runtime.h>
+
+#ifndef RT_BLOCK
+#define RT_BLOCK 256
+#endif
+#ifndef RT_RESERVE
+#define RT_RESERVE 128u   // pixel slots a warp reserves per atomicAdd (multiple of 32)
+#endif
+
+namespace rt {
+
+// --- TMA bulk copy (global -> shared) of the hot primitive list -------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void stage_scene_tma(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                                unsigned long long* mbar)
+{
+    const uint32_t bar = smem_u32(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                     : "memory");
+        uint32_t       dst = smem_u32(smem_dst);
+        const char*    src = static_cast<const char*>(gmem_src);
+        uint32_t       off = 0;
+        const uint32_t CH  = 32768u;   // keep each bulk copy modest; all complete on one barrier
+        while (off < bytes) {
+            uint32_t n = bytes - off < CH ? bytes - off : CH;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(dst + off), "l"(src + off), "r"(n), "r"(bar)
+                : "memory");
+            off += n;
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(0)
+            : "memory");
+    }
+}
+
+// Decode a pixel slot of this launch's (padded) work space into image coordinates.
+// Work space: n_tiles strips of tile_rows x Wpad pixels, each strip cut into 8x4 sub-tiles.
+struct PixelSlot {
+    uint32_t column;
+    uint32_t image_row;   // 0 = top row of the frame
+    uint32_t out_index;   // index into out / accum
+    bool     valid;
+};
+
+__device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_t slot, uint32_t subtiles_x,
+                                                 uint32_t chunks_per_strip)
+{
+    const uint32_t chunk = slot >> 5, in = slot & 31u;
+    const uint32_t strip = chunk / chunks_per_strip;
+    const uint32_t c     = chunk - strip * chunks_per_strip;
+    const uint32_t sy    = c / subtiles_x;
+    const uint32_t sx    = c - sy * subtiles_x;
+    const uint32_t x     = sx * 8u + (in & 7u);
+    const uint32_t yin   = sy * 4u + (in >> 3);
+    const uint32_t tile  = P.tile_first + strip * P.tile_stride;
+    PixelSlot s;
+    s.column    = x;
+    s.image_row = tile * P.tile_rows + yin;
+    s.valid     = (x < P.width) && (s.image_row < P.height);
+    const uint32_t out_row = (P.flags & RT_FLAG_COMPACT_OUT) ? strip * P.tile_rows + yin : s.image_row;
+    s.out_index = out_row * P.width + x;
+    return s;
+}
+
+template <bool FAST, bool SMEM>
+__global__ void __launch_bounds__(RT_BLOCK) rt_render_kernel(const __grid_constant__ RtFrameParams P,
+                                                            const __grid_constant__ RtSceneView  G)
+{
+    extern __shared__ __align__(128) unsigned char rt_smem[];
+    __shared__ __align__(8) unsigned long long rt_mbar;
+
+    const RtFloat4* sph;
+    const RtFloat4* tri_plane;
+    if (SMEM) {
+        const uint32_t hot_bytes = (G.n_sph + G.n_tri) * (uint32_t)sizeof(RtFloat4);
+        if (hot_bytes) stage_scene_tma(rt_smem, G.sph, hot_bytes, &rt_mbar);   // sph | tri_plane contiguous
+        sph       = reinterpret_cast<const RtFloat4*>(rt_smem);
+        tri_plane = sph + G.n_sph;
+    } else {
+        sph       = G.sph;
+        tri_plane = G.tri_plane;
+    }
+
+    const uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt   = (1u << lane) - 1u;
+
+    const uint32_t subtiles_x       = (P.width + 7u) >> 3;
+    const uint32_t chunks_per_strip = subtiles_x * (P.tile_rows >> 2);
+    const uint32_t total_slots      = P.n_tiles * chunks_per_strip * 32u;
+    const bool     trace            = (P.spp > 0) && (P.depth > 0);
+
+    // warp-uniform slab of reserved pixel slots
+    uint32_t pool_next = 0, pool_end = 0;
+    bool     exhausted = false;
+
+    // per-lane pixel state
+    bool     have = false;
+    uint32_t column = 0, ref_row = 0, out_index = 0;
+    int32_t  sample = 0;
+    float    acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_a = 0.f;
+    Path     path;
+    path.seg_left = 0;
+    path.rng      = 1u;
+    path.o = path.d = path.thr = mk(0.f, 0.f, 0.f);
+    uint32_t segments = 0;
+
+    for (;;) {
+        // ---- 1. lanes without a pixel take the next slots of the warp's slab ----
+        uint32_t need = __ballot_sync(FULL, !have);
+        while (need && !exhausted) {
+            if (pool_next == pool_end) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(P.work_counter, RT_RESERVE);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= total_slots) { exhausted = true; break; }
+                pool_next = base;
+                pool_end  = min(base + RT_RESERVE, total_slots);
+            }
+            const uint32_t avail = pool_end - pool_next;
+            const uint32_t rank  = __popc(need & lt);
+            if (!have && rank < avail) {
+                PixelSlot s = decode_slot(P, pool_next + rank, subtiles_x, chunks_per_strip);
+                if (s.valid) {
+                    column    = s.column;
+                    ref_row   = P.height - 1u - s.image_row;        // common.rs:351 (vertical flip)
+                    out_index = s.out_index;
+                    sample    = 0;
+                    path.seg_left = 0;
+                    if (P.flags & RT_FLAG_ACCUM_IN) {
+                        RtFloat4 a = ld4(&P.accum[out_index]);
+                        acc_r = a.x; acc_g = a.y; acc_b = a.z; acc_a = a.w;
+                    } else {
+                        acc_r = acc_g = acc_b = 0.f; acc_a = 1.f;   // Color::new(0,0,0), common.rs:333
+                    }
+                    have = true;
+                }
+            }
+            pool_next += min(avail, (uint32_t)__popc(need));
+            need = __ballot_sync(FULL, !have);
+        }
+        if (__ballot_sync(FULL, have) == 0u) break;
+
+        bool finished_sample = false;
+        V3   colour = mk(0.f, 0.f, 0.f);
+
+        if (have && trace) {
+            // ---- 2. start the next sample of this lane's pixel ----
+            if (path.seg_left == 0) start_sample<FAST>(path, P, column, ref_row, (uint32_t)(P.sample_begin + sample));
+
+            // ---- 3. one ray segment: World::hit + scatter ----
+            Hit h = closest_hit<FAST>(sph, G.n_sph, tri_plane, G.tri_v, G.n_tri, path.o, path.d);
+            ++segments;
+            if (shade<FAST>(G, sph, path, h, colour)) {
+                if (--path.seg_left == 0) { finished_sample = true; colour = mk(0.f, 0.f, 0.f); }   // common.rs:284
+            } else {
+                finished_sample = true;
+            }
+        }
+
+        // ---- 4. accumulate in sample order; resolve + pack when the pixel is complete ----
+        if (have) {
+            if (finished_sample) {
+                acc_r += colour.x; acc_g += colour.y; acc_b += colour.z; acc_a += 1.0f;   // add_with_alpha
+                path.seg_left = 0;
+                ++sample;
+            }
+            if (!trace || sample >= P.spp) {
+                if (!trace && P.spp > 0) acc_a += (float)P.spp;   // depth <= 0: spp black samples, alpha 1 each
+                if (P.flags & RT_FLAG_ACCUM_OUT) {
+                    float4 a = make_float4(acc_r, acc_g, acc_b, acc_a);
+                    *reinterpret_cast<float4*>(&P.accum[out_index]) = a;
+                }
+                if (!(P.flags & RT_FLAG_NO_RESOLVE))
+                    P.out[out_index] = resolve_pixel<FAST>(acc_r, acc_g, acc_b, acc_a, P.resolve_spp);
+                have = false;
+            }
+        }
+    }
+
+    // ray-segment count: one atomic per warp
+    unsigned long long segs = segments;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
+    if (lane == 0 && P.ray_counter && segs) atomicAdd(P.ray_counter, segs);
+}
+
+// Host-side launcher for one policy.
+template <bool FAST>
+cudaError_t launch_render(const RtFrameParams& P, const RtSceneView& G, int grid, size_t smem_limit,
+                          cudaStream_t stream)
+{
+    const size_t hot_bytes = (size_t)(G.n_sph + G.n_tri) * sizeof(RtFloat4);
+    cudaError_t  e;
+    if (hot_bytes <= smem_limit) {
+        auto k = rt_render_kernel<FAST, true>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+        if (e != cudaSuccess) return e;
+        k<<<grid, RT_BLOCK, hot_bytes, stream>>>(P, G);
+    } else {
+        auto k = rt_render_kernel<FAST, false>;
+        k<<<grid, RT_BLOCK, 0, stream>>>(P, G);
+    }
+    return cudaGetLastError();
+}
+
+template <bool FAST>
+cudaError_t render_occupancy(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm)
+{
+    if (hot_bytes <= smem_limit) {
+        auto k = rt_render_kernel<FAST, true>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, RT_BLOCK, hot_bytes);
+    }
+    auto k = rt_render_kernel<FAST, false>;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, RT_BLOCK, 0);
+}
+
+}   // namespace rt

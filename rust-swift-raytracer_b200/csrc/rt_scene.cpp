@@ -1,0 +1,475 @@
+// rt_scene.cpp — host-side scene construction for the render path: camera constructors,
+// triangle precomputation, SoA packing (kernel K1 of SURVEY.md §2a is a single H2D copy of
+// the blob built here), the world-text parser that load_world() needs, and the PPM writer.
+//
+// Compiled with -ffp-contract=off: every value computed here (camera vectors, r*r, triangle
+// normals, plane constants) must carry exactly the bits the reference's Rust code computes.
+#include "rt_host.hpp"
+
+#include <clocale>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <locale.h>
+#include <string_view>
+#include <unordered_map>
+
+namespace rt {
+
+namespace {
+
+struct F3 { float x, y, z; };
+inline F3 f3(RtVec3 v) { return {v.x, v.y, v.z}; }
+inline RtVec3 rv(F3 v) { return {v.x, v.y, v.z}; }
+inline F3 sub(F3 a, F3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline F3 add(F3 a, F3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline F3 scale(F3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline F3 divide(F3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+inline float dot3(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// maths.rs:88-94
+inline F3 cross3(F3 a, F3 b) { return {a.y * b.z - a.z * b.y, -(a.x * b.z - a.z * b.x), a.x * b.y - a.y * b.x}; }
+// maths.rs:111-118
+inline F3 unit(F3 a)
+{
+    float len = std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z);
+    return {a.x / len, a.y / len, a.z / len};
+}
+inline bool tiny(F3 a) { return std::fabs(a.x) < 1e-8f && std::fabs(a.y) < 1e-8f && std::fabs(a.z) < 1e-8f; }
+
+}   // namespace
+
+// ------------------------------------------------------------------ camera.rs
+
+Camera Camera::new_at(RtVec3 origin, float aspect_ratio)
+{
+    const float viewport_height = 2.0f;
+    const float viewport_width  = aspect_ratio * viewport_height;
+    const float focal_length    = 1.0f;
+    Camera c;
+    c.d.origin            = origin;
+    c.d.horizontal        = {viewport_width, 0.0f, 0.0f};
+    c.d.vertical          = {0.0f, viewport_height, 0.0f};
+    c.d.lower_left_corner = rv(sub(f3(origin), F3{viewport_width / 2.0f, viewport_height / 2.0f, focal_length}));
+    return c;
+}
+
+Camera Camera::new_with_vertical_fov(RtVec3 origin, float vfov, float aspect_ratio)
+{
+    const float h               = std::tan(vfov / 2.0f);
+    const float viewport_height = 2.0f * h;
+    const float viewport_width  = aspect_ratio * viewport_height;
+    const float focal_length    = 1.0f;
+    Camera c;
+    c.d.origin            = origin;
+    c.d.horizontal        = {viewport_width, 0.0f, 0.0f};
+    c.d.vertical          = {0.0f, viewport_height, 0.0f};
+    c.d.lower_left_corner = rv(sub(f3(origin), F3{viewport_width / 2.0f, viewport_height / 2.0f, focal_length}));
+    return c;
+}
+
+bool Camera::new_look_at(RtVec3 origin, RtVec3 look_at, RtVec3 up_in, float vfov, float aspect_ratio,
+                         Camera* out, std::string* error)
+{
+    if (tiny(sub(f3(origin), f3(look_at)))) {                       // camera.rs:50
+        if (error) *error = "Origin and look_at must differ!";
+        return false;
+    }
+    const float viewport_height = 2.0f * std::tan(vfov / 2.0f);
+    const float viewport_width  = viewport_height * aspect_ratio;
+
+    const F3 up = unit(f3(up_in));                                  // `up: NVec3` is unit by construction
+    const F3 w  = unit(sub(f3(origin), f3(look_at)));
+    const F3 u  = cross3(up, w);                                    // NVec3::cross: not re-normalised
+    const F3 v  = cross3(w, u);
+    if (!(std::fabs(v.y) > 1e-8f)) {                                // camera.rs:62
+        if (error) *error = "Origin and look_at can't have the same z-coordinate.";
+        return false;
+    }
+    const F3 horizontal = scale(u, viewport_width);
+    const F3 vertical   = scale(v, viewport_height);
+    out->d.origin       = origin;
+    out->d.horizontal   = rv(horizontal);
+    out->d.vertical     = rv(vertical);
+    out->d.lower_left_corner =
+        rv(sub(sub(sub(f3(origin), divide(horizontal, 2.0f)), divide(vertical, 2.0f)), w));
+    return true;
+}
+
+Camera Camera::moved(float x, float y, float z) const
+{
+    return Camera::new_at(rv(add(f3(d.origin), F3{x, y, z})), aspect_ratio());
+}
+
+// ----------------------------------------------------------------- common.rs
+
+Triangle Triangle::make(RtVec3 v0, RtVec3 v1, RtVec3 v2, const Material& m)
+{
+    const F3 a = sub(f3(v1), f3(v0));
+    const F3 b = sub(f3(v2), f3(v0));
+    Triangle t;
+    t.v0 = v0; t.v1 = v1; t.v2 = v2;
+    t.normal   = rv(unit(cross3(a, b)));
+    t.material = m;
+    return t;
+}
+
+std::unique_ptr<World> World::make(std::vector<Sphere> spheres, std::vector<Triangle> triangles)
+{
+    auto w = std::make_unique<World>();
+    w->spheres   = std::move(spheres);
+    w->triangles = std::move(triangles);
+    return w;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+RtSceneView World::Packed::view(const unsigned char* base) const
+{
+    RtSceneView v;
+    v.sph       = reinterpret_cast<const RtFloat4*>(base + off_sph);
+    v.tri_plane = reinterpret_cast<const RtFloat4*>(base + off_tri_plane);
+    v.tri_v     = reinterpret_cast<const RtFloat4*>(base + off_tri_v);
+    v.mat       = reinterpret_cast<const RtFloat4*>(base + off_mat);
+    v.sph_r     = reinterpret_cast<const float*>(base + off_sph_r);
+    v.mat_type  = reinterpret_cast<const uint32_t*>(base + off_mat_type);
+    v.n_sph     = n_sph;
+    v.n_tri     = n_tri;
+    return v;
+}
+
+// Scene pack: AoS {Sphere, Triangle} -> the SoA blob of rt_types.h.
+const World::Packed& World::packed() const
+{
+    if (packed_) return *packed_;
+    auto p = std::make_unique<Packed>();
+    const size_t S = spheres.size(), T = triangles.size(), P = S + T;
+    p->n_sph = (uint32_t)S;
+    p->n_tri = (uint32_t)T;
+    size_t off = 0;
+    p->off_sph       = off; off += S * sizeof(RtFloat4);
+    p->off_tri_plane = off; off += T * sizeof(RtFloat4);
+    p->off_tri_v     = off; off += 3 * T * sizeof(RtFloat4);
+    p->off_mat       = off; off += P * sizeof(RtFloat4);
+    p->off_sph_r     = off; off += align_up(S * sizeof(float), 16);
+    p->off_mat_type  = off; off += align_up(P * sizeof(uint32_t), 16);
+    p->blob.assign(off ? off : 16, 0);
+    unsigned char* base = p->blob.data();
+    auto* sph   = reinterpret_cast<RtFloat4*>(base + p->off_sph);
+    auto* plane = reinterpret_cast<RtFloat4*>(base + p->off_tri_plane);
+    auto* triv  = reinterpret_cast<RtFloat4*>(base + p->off_tri_v);
+    auto* mat   = reinterpret_cast<RtFloat4*>(base + p->off_mat);
+    auto* sr    = reinterpret_cast<float*>(base + p->off_sph_r);
+    auto* mt    = reinterpret_cast<uint32_t*>(base + p->off_mat_type);
+    for (size_t i = 0; i < S; ++i) {
+        const Sphere& s = spheres[i];
+        sph[i] = {s.center.x, s.center.y, s.center.z, s.radius * s.radius};   // radius.powi(2), common.rs:77
+        sr[i]  = s.radius;
+        mat[i] = {s.material.r, s.material.g, s.material.b, s.material.param};
+        mt[i]  = (uint32_t)s.material.type;
+    }
+    for (size_t j = 0; j < T; ++j) {
+        const Triangle& t = triangles[j];
+        // common.rs:128-133,140: n = (v1-v0) x (v2-v0) and d = n.v0 depend on the triangle
+        // only, so they are evaluated once here with the reference's exact operation order.
+        const F3 n = cross3(sub(f3(t.v1), f3(t.v0)), sub(f3(t.v2), f3(t.v0)));
+        plane[j]        = {n.x, n.y, n.z, dot3(n, f3(t.v0))};
+        triv[3 * j + 0] = {t.v0.x, t.v0.y, t.v0.z, t.normal.x};
+        triv[3 * j + 1] = {t.v1.x, t.v1.y, t.v1.z, t.normal.y};
+        triv[3 * j + 2] = {t.v2.x, t.v2.y, t.v2.z, t.normal.z};
+        mat[S + j] = {t.material.r, t.material.g, t.material.b, t.material.param};
+        mt[S + j]  = (uint32_t)t.material.type;
+    }
+    packed_ = std::move(p);
+    return *packed_;
+}
+
+// ----------------------------------------------------------------- parser.rs
+
+const char* parse_error_name(ParseError e)
+{
+    switch (e) {
+    case ParseError::Ok: return "Ok";
+    case ParseError::CouldntOpenFile: return "Couldn't open file";
+    case ParseError::MissingCamera: return "Missing camera";
+    case ParseError::WrongSyntax: return "Wrong syntax";
+    case ParseError::DidntStartWith: return "Error. (DidntStartWith)";
+    case ParseError::NotAI32: return "Error. (NotAI32)";
+    case ParseError::NotAF32: return "Error. (NotAF32)";
+    case ParseError::InvalidUtf8: return "Invalid UTF-8";
+    }
+    return "Error.";
+}
+
+namespace {
+
+using sv = std::string_view;
+
+struct Fail { ParseError e; };   // thrown inside the parser only; never crosses parse_input
+
+// One Unicode scalar from valid UTF-8.
+inline size_t decode(sv s, uint32_t& cp)
+{
+    auto u = [&](size_t i) { return (uint32_t)(unsigned char)s[i]; };
+    if (u(0) < 0x80) { cp = u(0); return 1; }
+    if ((u(0) & 0xE0) == 0xC0 && s.size() >= 2) { cp = ((u(0) & 0x1F) << 6) | (u(1) & 0x3F); return 2; }
+    if ((u(0) & 0xF0) == 0xE0 && s.size() >= 3) { cp = ((u(0) & 0x0F) << 12) | ((u(1) & 0x3F) << 6) | (u(2) & 0x3F); return 3; }
+    if (s.size() >= 4) { cp = ((u(0) & 0x07) << 18) | ((u(1) & 0x3F) << 12) | ((u(2) & 0x3F) << 6) | (u(3) & 0x3F); return 4; }
+    cp = u(0);
+    return 1;
+}
+
+// char::is_whitespace (Unicode White_Space)
+inline bool is_space(uint32_t c)
+{
+    return (c >= 0x09 && c <= 0x0D) || c == 0x20 || c == 0x85 || c == 0xA0 || c == 0x1680 ||
+           (c >= 0x2000 && c <= 0x200A) || c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F || c == 0x3000;
+}
+
+bool valid_utf8(sv s)
+{
+    size_t i = 0, n = s.size();
+    while (i < n) {
+        unsigned char c = (unsigned char)s[i];
+        size_t len; uint32_t cp;
+        if (c < 0x80) { ++i; continue; }
+        if (c >= 0xC2 && c <= 0xDF) { len = 2; cp = c & 0x1F; }
+        else if (c >= 0xE0 && c <= 0xEF) { len = 3; cp = c & 0x0F; }
+        else if (c >= 0xF0 && c <= 0xF4) { len = 4; cp = c & 0x07; }
+        else return false;
+        if (i + len > n) return false;
+        for (size_t k = 1; k < len; ++k) {
+            unsigned char d = (unsigned char)s[i + k];
+            if ((d & 0xC0) != 0x80) return false;
+            cp = (cp << 6) | (d & 0x3F);
+        }
+        if (len == 3 && (cp < 0x800 || (cp >= 0xD800 && cp <= 0xDFFF))) return false;
+        if (len == 4 && (cp < 0x10000 || cp > 0x10FFFF)) return false;
+        i += len;
+    }
+    return true;
+}
+
+struct Cursor {
+    sv s;
+
+    void skip_whitespace()                                  // parser.rs:54-57
+    {
+        while (!s.empty()) {
+            uint32_t cp; size_t len = decode(s, cp);
+            if (!is_space(cp)) break;
+            s.remove_prefix(len);
+        }
+    }
+    // parser.rs:59-62.  ASCII [A-Za-z0-9_] (the reference accepts Unicode alphanumerics)
+    sv identifier()
+    {
+        size_t i = 0;
+        while (i < s.size()) {
+            unsigned char c = (unsigned char)s[i];
+            if ((c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_') ++i;
+            else break;
+        }
+        sv name = s.substr(0, i);
+        s.remove_prefix(i);
+        return name;
+    }
+    bool accept(sv target)                                  // parser.rs:82-89 as a predicate
+    {
+        if (s.size() >= target.size() && s.compare(0, target.size(), target) == 0) {
+            s.remove_prefix(target.size());
+            return true;
+        }
+        return false;
+    }
+    void expect(sv target) { if (!accept(target)) throw Fail{ParseError::DidntStartWith}; }
+
+    float number()                                          // parser.rs:107-133
+    {
+        if (s.size() < 3) throw Fail{ParseError::NotAF32};  // :112-114 (remaining *input* < 3 bytes)
+        size_t index = (s[0] == '-') ? 1 : 0, digits = 0;
+        bool   dot   = false;
+        for (; index < s.size(); ++index) {
+            char c = s[index];
+            if (c >= '0' && c <= '9') ++digits;
+            else if (c == '.') { if (dot) throw Fail{ParseError::NotAF32}; dot = true; }
+            else break;
+        }
+        if (!digits) throw Fail{ParseError::NotAF32};       // "", "-", ".", "-." fail str::parse::<f32>
+        std::string tok(s.substr(0, index));
+        static locale_t c_loc = newlocale(LC_ALL_MASK, "C", (locale_t)0);
+        float v = strtof_l(tok.c_str(), nullptr, c_loc);    // correctly rounded, as Rust's parse
+        s.remove_prefix(index);
+        return v;
+    }
+    RtVec3 vec3()                                           // parser.rs:135-142
+    {
+        RtVec3 v;
+        v.x = number(); skip_whitespace();
+        v.y = number(); skip_whitespace();
+        v.z = number();
+        return v;
+    }
+    void skip_comment()                                     // parser.rs:313-323
+    {
+        while (s.size() >= 2 && s[0] == '/' && s[1] == '/') {
+            size_t nl = s.find('\n', 2);
+            if (nl == sv::npos) throw Fail{ParseError::WrongSyntax};
+            s.remove_prefix(nl + 1);
+        }
+    }
+};
+
+struct SvHash { size_t operator()(sv v) const { return std::hash<sv>{}(v); } };
+using MaterialMap = std::unordered_map<sv, Material, SvHash>;
+
+bool statement_camera(Cursor& c, Camera& cam)               // parser.rs:145-167
+{
+    if (!c.accept("camera")) return false;
+    c.skip_whitespace(); c.expect("origin"); c.skip_whitespace();
+    RtVec3 o = c.vec3(); c.skip_whitespace();
+    c.expect("aspect"); c.skip_whitespace();
+    float a = c.number(); c.skip_whitespace();
+    c.expect(";");
+    cam = Camera::new_at(o, a);
+    return true;
+}
+
+bool statement_material(Cursor& c, MaterialMap& map)        // parser.rs:175-234
+{
+    if (!c.accept("material")) return false;
+    c.skip_whitespace();
+    sv name = c.identifier();
+    c.skip_whitespace(); c.expect(":"); c.skip_whitespace();
+    Material m;
+    if (c.accept("Diffuse")) {
+        c.skip_whitespace(); c.expect("color"); c.skip_whitespace();
+        RtVec3 col = c.vec3(); c.skip_whitespace();
+        c.expect(";");
+        m = Material::Diffuse(col.x, col.y, col.z);
+    } else if (c.accept("Metal")) {
+        c.skip_whitespace(); c.expect("color"); c.skip_whitespace();
+        RtVec3 col = c.vec3(); c.skip_whitespace();
+        c.expect("fuzz"); c.skip_whitespace();
+        float f = c.number(); c.skip_whitespace();
+        c.expect(";");
+        m = Material::Metal(col.x, col.y, col.z, f);
+    } else if (c.accept("Dielectric")) {
+        c.skip_whitespace(); c.expect("ir"); c.skip_whitespace();
+        float ir = c.number(); c.skip_whitespace();
+        c.expect(";");
+        m = Material::Dielectric(ir);
+    } else {
+        throw Fail{ParseError::WrongSyntax};
+    }
+    map[name] = m;                                          // HashMap::insert: last definition wins
+    return true;
+}
+
+const Material& lookup(const MaterialMap& map, sv name)
+{
+    auto it = map.find(name);
+    if (it == map.end()) throw Fail{ParseError::WrongSyntax};   // parser.rs:259, :299
+    return it->second;
+}
+
+bool statement_sphere(Cursor& c, const MaterialMap& map, std::vector<Sphere>& out)   // parser.rs:237-269
+{
+    if (!c.accept("sphere")) return false;
+    c.skip_whitespace(); c.expect("center"); c.skip_whitespace();
+    RtVec3 center = c.vec3(); c.skip_whitespace();
+    c.expect("radius"); c.skip_whitespace();
+    float r = c.number(); c.skip_whitespace();
+    c.expect("material"); c.skip_whitespace();
+    sv name = c.identifier(); c.skip_whitespace();
+    c.expect(";");
+    out.push_back(Sphere{center, r, lookup(map, name)});
+    return true;
+}
+
+bool statement_triangle(Cursor& c, const MaterialMap& map, std::vector<Triangle>& out)   // parser.rs:272-310
+{
+    if (!c.accept("triangle")) return false;
+    c.skip_whitespace(); c.expect("v0"); c.skip_whitespace();
+    RtVec3 v0 = c.vec3(); c.skip_whitespace();
+    c.expect("v1"); c.skip_whitespace();
+    RtVec3 v1 = c.vec3(); c.skip_whitespace();
+    c.expect("v2"); c.skip_whitespace();
+    RtVec3 v2 = c.vec3(); c.skip_whitespace();
+    c.expect("material"); c.skip_whitespace();
+    sv name = c.identifier(); c.skip_whitespace();
+    c.expect(";");
+    out.push_back(Triangle::make(v0, v1, v2, lookup(map, name)));
+    return true;
+}
+
+}   // namespace
+
+ParseResult parse_input(const char* source, size_t length)
+{
+    ParseResult res;
+    sv text(source, length);
+    if (!valid_utf8(text)) { res.error = ParseError::InvalidUtf8; return res; }   // lib.rs:40 to_str()
+    try {
+        Cursor c{text};
+        MaterialMap           materials;
+        std::vector<Sphere>   spheres;
+        std::vector<Triangle> triangles;
+
+        c.skip_comment();                                                  // :342
+        if (!statement_camera(c, res.camera)) throw Fail{ParseError::MissingCamera};
+        c.skip_whitespace();
+        c.skip_comment();                                                  // :353
+        while (statement_material(c, materials)) { c.skip_whitespace(); c.skip_comment(); }
+        while (statement_sphere(c, materials, spheres)) { c.skip_whitespace(); c.skip_comment(); }
+        while (statement_triangle(c, materials, triangles)) { c.skip_whitespace(); c.skip_comment(); }
+        if (!c.s.empty()) throw Fail{ParseError::WrongSyntax};             // :377-378
+        res.world = World::make(std::move(spheres), std::move(triangles));
+    } catch (const Fail& f) {
+        res.error = f.e;
+        res.world.reset();
+    }
+    return res;
+}
+
+// ------------------------------------------------------------------ image.rs
+
+bool write_image(const Framebuffer& fb, const char* path)   // image.rs:59-81 (ASCII P3)
+{
+    FILE* f = path ? std::fopen(path, "w") : stdout;
+    if (!f) return false;
+    std::string buf;
+    buf.reserve(fb.pixels.size() * 12 + 32);
+    char line[64];
+    int  n = std::snprintf(line, sizeof line, "P3\n%zu %zu\n%d\n", fb.width, fb.height, 255);
+    buf.append(line, (size_t)n);
+    for (const ColorU8& c : fb.pixels) {
+        n = std::snprintf(line, sizeof line, "%u %u %u\n", c.r, c.g, c.b);
+        buf.append(line, (size_t)n);
+    }
+    bool ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    if (path) ok = (std::fclose(f) == 0) && ok;
+    return ok;
+}
+
+bool write_image_p6(const Framebuffer& fb, const char* path)
+{
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return false;
+    std::fprintf(f, "P6\n%zu %zu\n255\n", fb.width, fb.height);
+    std::vector<unsigned char> rgb(fb.pixels.size() * 3);
+    for (size_t i = 0; i < fb.pixels.size(); ++i) {
+        rgb[3 * i + 0] = fb.pixels[i].r; rgb[3 * i + 1] = fb.pixels[i].g; rgb[3 * i + 2] = fb.pixels[i].b;
+    }
+    bool ok = std::fwrite(rgb.data(), 1, rgb.size(), f) == rgb.size();
+    return (std::fclose(f) == 0) && ok;
+}
+
+uint32_t shard_tile_count(uint32_t height, uint32_t tile_rows, uint32_t index, uint32_t count)
+{
+    const uint32_t tiles = (height + tile_rows - 1) / tile_rows;
+    if (index >= tiles) return 0;
+    return (tiles - index + count - 1) / count;
+}
+
+}   // namespace rt

@@ -1,0 +1,63 @@
+// hostsim.cpp — TEST-ONLY: compiles the device header csrc/rt_trace.cuh (exact policy) with
+// g++ and drives it with a plain per-pixel loop, so that the shading / intersection / RNG
+// logic of the CUDA kernel can be checked against the oracle on a machine without a GPU.
+// It is NOT part of the product and is never loaded by the package: the shipped library has
+// no CPU render path.  Only tests/test_hostsim.py loads it.
+#define RT_TU_EXACT 1
+#include "../../rust-swift-raytracer_b200/csrc/rt_trace.cuh"
+#include "../../rust-swift-raytracer_b200/csrc/rt_host.hpp"
+
+#include <cstring>
+
+namespace rt {
+struct DeviceScene {};
+World::World()  = default;
+World::~World() = default;
+void World::invalidate_device() { packed_.reset(); }
+}   // namespace rt
+
+extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uint32_t W, uint32_t H, int32_t spp,
+                              int32_t depth, uint32_t seed, uint32_t flags, int32_t sample_begin,
+                              int32_t resolve_spp, uint8_t* out, uint64_t* rays_out)
+{
+    using namespace rt;
+    ParseResult pr = parse_input(scene_text, std::strlen(scene_text));
+    if (pr.error != ParseError::Ok) return (int)pr.error;
+    const World::Packed& pk = pr.world->packed();
+    RtSceneView G = pk.view(pk.blob.data());
+
+    RtFrameParams P{};
+    std::memcpy(&P.camera, cam12, sizeof(float) * 12);
+    P.width = W; P.height = H; P.spp = spp; P.depth = depth; P.seed = seed; P.flags = flags;
+    P.sample_begin = sample_begin;
+    P.resolve_spp  = resolve_spp ? resolve_spp : sample_begin + spp;
+
+    uint64_t rays = 0;
+    uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
+    const bool trace = spp > 0 && depth > 0;
+    for (uint32_t image_row = 0; image_row < H; ++image_row)
+        for (uint32_t column = 0; column < W; ++column) {
+            const uint32_t ref_row = H - 1u - image_row;
+            float r = 0.f, g = 0.f, b = 0.f, a = 1.f;
+            if (trace) {
+                for (int32_t s = 0; s < spp; ++s) {
+                    Path path;
+                    start_sample<false>(path, P, column, ref_row, (uint32_t)(sample_begin + s));
+                    V3 colour = mk(0.f, 0.f, 0.f);
+                    for (;;) {
+                        Hit h = closest_hit<false>(G.sph, G.n_sph, G.tri_plane, G.tri_v, G.n_tri, path.o, path.d);
+                        ++rays;
+                        if (shade<false>(G, G.sph, path, h, colour)) {
+                            if (--path.seg_left == 0) { colour = mk(0.f, 0.f, 0.f); break; }
+                        } else break;
+                    }
+                    r += colour.x; g += colour.y; b += colour.z; a += 1.0f;
+                }
+            } else if (spp > 0) {
+                a += (float)spp;
+            }
+            out32[image_row * W + column] = resolve_pixel<false>(r, g, b, a, P.resolve_spp);
+        }
+    if (rays_out) *rays_out = rays;
+    return 0;
+}
