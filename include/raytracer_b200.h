@@ -104,6 +104,11 @@ int rt_world_add_triangle(struct Rust_WorldHandle *handle, const float v0[3], co
                           const float v2[3], uint32_t material, const float color[3], float param);
 size_t rt_world_sphere_count(const struct Rust_WorldHandle *handle);
 size_t rt_world_triangle_count(const struct Rust_WorldHandle *handle);
+/* Read back primitive `index` in list (= hit-test) order.  out9: center[3], radius,
+ * material type (as float), color[3], param.  out18: v0[3], v1[3], v2[3], stored normal[3],
+ * material type, color[3], param, 0.  Return 0 on success. */
+int rt_world_get_sphere(const struct Rust_WorldHandle *handle, size_t index, float out9[9]);
+int rt_world_get_triangle(const struct Rust_WorldHandle *handle, size_t index, float out18[18]);
 
 /* image.rs:59-81: ASCII PPM (P3), and a binary P6 variant.  Return 0 on success. */
 int rt_write_image(struct Rust_CFramebuffer framebuffer, const char *path);

@@ -83,7 +83,8 @@ EXPORTED_SYMBOLS = (
     "render_with_options", "rt_render_device", "rt_shard_pixel_count",
     "rt_set_camera_at", "rt_set_camera_vertical_fov", "rt_set_camera_look_at", "rt_get_camera",
     "rt_camera_aspect_ratio", "rt_world_new", "rt_world_add_sphere", "rt_world_add_triangle",
-    "rt_world_sphere_count", "rt_world_triangle_count", "rt_write_image", "rt_write_image_p6",
+    "rt_world_sphere_count", "rt_world_triangle_count", "rt_world_get_sphere", "rt_world_get_triangle",
+    "rt_write_image", "rt_write_image_p6",
     "rt_alloc_pixels", "rt_free_pixels", "rt_measure_fp32_peak",
 )
 
@@ -139,6 +140,10 @@ def lib() -> C.CDLL:
     L.rt_world_sphere_count.argtypes = [hp]
     L.rt_world_triangle_count.restype = C.c_size_t
     L.rt_world_triangle_count.argtypes = [hp]
+    L.rt_world_get_sphere.restype = C.c_int
+    L.rt_world_get_sphere.argtypes = [hp, C.c_size_t, f3]
+    L.rt_world_get_triangle.restype = C.c_int
+    L.rt_world_get_triangle.argtypes = [hp, C.c_size_t, f3]
     L.rt_write_image.restype = C.c_int
     L.rt_write_image.argtypes = [_CFramebuffer, C.c_char_p]
     L.rt_write_image_p6.restype = C.c_int
@@ -253,6 +258,20 @@ class WorldHandle:
     @property
     def n_triangles(self) -> int:
         return lib().rt_world_triangle_count(self.ptr)
+
+    def sphere(self, index: int) -> np.ndarray:
+        """center[3], radius, material type, color[3], param"""
+        out = (C.c_float * 9)()
+        if lib().rt_world_get_sphere(self.ptr, index, out):
+            raise IndexError(index)
+        return np.array(out, dtype=np.float32)
+
+    def triangle(self, index: int) -> np.ndarray:
+        """v0[3], v1[3], v2[3], normal[3], material type, color[3], param, 0"""
+        out = (C.c_float * 18)()
+        if lib().rt_world_get_triangle(self.ptr, index, out):
+            raise IndexError(index)
+        return np.array(out, dtype=np.float32)
 
     def add_sphere(self, center, radius, material=DIFFUSE, color=(1.0, 1.0, 1.0), param=0.0):
         if lib().rt_world_add_sphere(self.ptr, _f3(center), float(radius), int(material), _f3(color), float(param)):

@@ -234,6 +234,26 @@ int rt_world_add_triangle(Rust_WorldHandle* h, const float v0[3], const float v1
 size_t rt_world_sphere_count(const Rust_WorldHandle* h) { return (h && h->world) ? h->world->world->spheres.size() : 0; }
 size_t rt_world_triangle_count(const Rust_WorldHandle* h) { return (h && h->world) ? h->world->world->triangles.size() : 0; }
 
+int rt_world_get_sphere(const Rust_WorldHandle* h, size_t i, float out[9])
+{
+    if (!h || !h->world || i >= h->world->world->spheres.size()) return 1;
+    const rt::Sphere& s = h->world->world->spheres[i];
+    const float v[9] = {s.center.x, s.center.y, s.center.z, s.radius, (float)s.material.type,
+                        s.material.r, s.material.g, s.material.b, s.material.param};
+    std::memcpy(out, v, sizeof v);
+    return 0;
+}
+int rt_world_get_triangle(const Rust_WorldHandle* h, size_t i, float out[18])
+{
+    if (!h || !h->world || i >= h->world->world->triangles.size()) return 1;
+    const rt::Triangle& t = h->world->world->triangles[i];
+    const float v[18] = {t.v0.x, t.v0.y, t.v0.z, t.v1.x, t.v1.y, t.v1.z, t.v2.x, t.v2.y, t.v2.z,
+                         t.normal.x, t.normal.y, t.normal.z, (float)t.material.type,
+                         t.material.r, t.material.g, t.material.b, t.material.param, 0.f};
+    std::memcpy(out, v, sizeof v);
+    return 0;
+}
+
 static int write_any(Rust_CFramebuffer fb, const char* path, bool p6)
 {
     return guarded([&] {
