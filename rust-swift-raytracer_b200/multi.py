@@ -65,3 +65,57 @@ def gather_frame(local: torch.Tensor, width: int, height: int, tile_rows: int, r
         return frame.view(height, width)
     dist.gather(local, gather_list=None, dst=dst, group=group)
     return None
+
+
+class ShardedRenderer:
+    """One rank's share of a tile-sharded frame, device-resident.
+
+    Every rank renders tiles rank, rank+world, ... of the frame into its compact RGBA8 buffer —
+    optionally as several progressive passes through a float4 accumulator that never leaves the
+    GPU — and the finished tiles are gathered to rank 0 (the only collective).  All kernels and
+    the gather are enqueued on torch's current CUDA stream, so CUDA events recorded on that
+    stream bracket the whole step.
+    """
+
+    def __init__(self, rt, handle, width: int, height: int, rank: int = 0, world: int = 1,
+                 tile_rows: int = 16, device=None):
+        self.rt, self.handle = rt, handle
+        self.width, self.height, self.rank, self.world, self.tile_rows = width, height, rank, world, tile_rows
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.local = alloc_compact(width, height, tile_rows, world, self.device)
+        self.accum: Optional[torch.Tensor] = None
+        j = padded_tiles_per_rank(height, tile_rows, world)
+        self.staging = (torch.empty((world, j * tile_rows * width), dtype=torch.int32, device=self.device)
+                        if (world > 1 and rank == 0) else None)
+        self.host_frame = (torch.empty((height, width), dtype=torch.int32).pin_memory() if rank == 0 else None)
+
+    def render(self, spp: int, depth: int, passes: int = 1, seed: Optional[int] = None, fast_math: bool = False,
+               fixed_jitter: bool = False, to_host: bool = False, count_rays: bool = False):
+        """Returns (frame, rays): frame is the [H, W] int32 RGBA8 frame on rank 0 (device tensor, or
+        the pinned host tensor when to_host) and None elsewhere; rays is this rank's ray-segment
+        count when count_rays (that mode synchronises after every pass), else 0."""
+        rt = self.rt
+        assert passes >= 1 and spp % passes == 0, "spp must divide evenly into passes"
+        if passes > 1 and self.accum is None:
+            self.accum = torch.empty((self.local.numel(), 4), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        per, rays = spp // passes, 0
+        for p in range(passes):
+            last = p == passes - 1
+            o = rt.Options(per, depth, sample_begin=p * per, resolve_spp=spp, fast_math=fast_math,
+                           fixed_jitter=fixed_jitter, tile_rows=self.tile_rows, shard_index=self.rank,
+                           shard_count=self.world, accum_in=p > 0, accum_out=not last, no_resolve=not last)
+            if seed is not None:
+                o.seed = seed
+            st = rt.RenderStats() if count_rays else None
+            rt.render_device(self.handle, o, self.width, self.height, self.local.data_ptr(),
+                             self.accum.data_ptr() if self.accum is not None else 0, stream, st)
+            if st is not None:
+                rays += st.rays
+        frame = gather_frame(self.local, self.width, self.height, self.tile_rows, self.rank, self.world,
+                             staging=self.staging)
+        if to_host and frame is not None:
+            self.host_frame.copy_(frame, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            frame = self.host_frame
+        return frame, rays
