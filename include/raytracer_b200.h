@@ -37,6 +37,8 @@ typedef struct RtRenderStats {
   uint32_t grid;        /* CTAs of the persistent launch */
   uint32_t smem_bytes;  /* primitive-list bytes staged per CTA */
   uint32_t resident;    /* 1: primitive list lives in shared memory */
+  uint32_t block;       /* threads per CTA */
+  uint32_t reserved;
 } RtRenderStats;
 
 /* common.rs:289-294 `Options`, extended.  Zero-initialise, then set struct_size. */
@@ -121,6 +123,11 @@ void                 rt_free_pixels(struct Rust_ColorU8 *pixels);
 /* FFMA-chain microbenchmark: measured FP32 peak of `device` in TFLOP/s (the roofline
  * denominator of the render kernel).  Negative on failure. */
 double rt_measure_fp32_peak(int device);
+
+/* GPU self-test: the exact kernel's shared-reciprocal divide (three numerators, one divisor)
+ * against the compiler's IEEE divide on `operand_sets` pseudo-random operand sets.  Returns
+ * the number of sets whose quotients differ in any bit (0 expected), negative on failure. */
+long long rt_selftest_division(int device, unsigned long long operand_sets, uint32_t seed);
 
 #ifdef __cplusplus
 }

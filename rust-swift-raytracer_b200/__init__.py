@@ -60,7 +60,8 @@ class _WorldHandle(C.Structure):   # lib.rs:29-33
 class RenderStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("kernel_ms", C.c_float),
                 ("total_ms", C.c_float), ("launches", C.c_uint32), ("grid", C.c_uint32),
-                ("smem_bytes", C.c_uint32), ("resident", C.c_uint32)]
+                ("smem_bytes", C.c_uint32), ("resident", C.c_uint32), ("block", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -85,7 +86,7 @@ EXPORTED_SYMBOLS = (
     "rt_camera_aspect_ratio", "rt_world_new", "rt_world_add_sphere", "rt_world_add_triangle",
     "rt_world_sphere_count", "rt_world_triangle_count", "rt_world_get_sphere", "rt_world_get_triangle",
     "rt_write_image", "rt_write_image_p6",
-    "rt_alloc_pixels", "rt_free_pixels", "rt_measure_fp32_peak",
+    "rt_alloc_pixels", "rt_free_pixels", "rt_measure_fp32_peak", "rt_selftest_division",
 )
 
 
@@ -154,6 +155,8 @@ def lib() -> C.CDLL:
     L.rt_free_pixels.argtypes = [C.c_void_p]
     L.rt_measure_fp32_peak.restype = C.c_double
     L.rt_measure_fp32_peak.argtypes = [C.c_int]
+    L.rt_selftest_division.restype = C.c_longlong
+    L.rt_selftest_division.argtypes = [C.c_int, C.c_ulonglong, C.c_uint32]
     _lib = L
     return L
 
@@ -378,6 +381,14 @@ def write_image(framebuffer: Framebuffer, path: str, binary: bool = False) -> No
 
 def measure_fp32_peak(device: int = -1) -> float:
     v = lib().rt_measure_fp32_peak(device)
+    if v < 0:
+        raise RenderError(last_error())
+    return v
+
+
+def selftest_division(operand_sets: int = 1 << 28, seed: int = 1, device: int = -1) -> int:
+    """Mismatches between the exact kernel's shared-reciprocal divide and the IEEE divide."""
+    v = lib().rt_selftest_division(device, int(operand_sets), int(seed) & 0xFFFFFFFF)
     if v < 0:
         raise RenderError(last_error())
     return v

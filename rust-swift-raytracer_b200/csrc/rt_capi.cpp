@@ -47,6 +47,7 @@ void export_stats(const rt::RenderStats& s, RtRenderStats* out)
 {
     out->rays = s.rays; out->samples = s.samples; out->kernel_ms = s.kernel_ms; out->total_ms = s.total_ms;
     out->launches = s.launches; out->grid = s.grid; out->smem_bytes = s.smem_bytes; out->resident = s.resident;
+    out->block = s.block; out->reserved = 0;
 }
 
 template <class F>
@@ -281,6 +282,13 @@ double rt_measure_fp32_peak(int device)
 {
     double v = -1.0;
     guarded([&] { v = rt::measure_fp32_peak_tflops(device, nullptr); });
+    return v;
+}
+
+long long rt_selftest_division(int device, unsigned long long operand_sets, uint32_t seed)
+{
+    long long v = -1;
+    guarded([&] { v = rt::selftest_division(device, operand_sets, seed); });
     return v;
 }
 

@@ -21,8 +21,10 @@ namespace rt {
 // defined in rt_kernels_exact.cu / rt_kernels_fast.cu
 cudaError_t launch_render_exact(const RtFrameParams&, const RtSceneView&, int grid, size_t smem_limit, cudaStream_t);
 cudaError_t launch_render_fast(const RtFrameParams&, const RtSceneView&, int grid, size_t smem_limit, cudaStream_t);
-cudaError_t occupancy_exact(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm);
-cudaError_t occupancy_fast(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm);
+cudaError_t occupancy_exact(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm, int* block_size);
+cudaError_t occupancy_fast(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm, int* block_size);
+cudaError_t launch_selftest_division(unsigned long long n_per_thread, uint32_t seed, int grid, int block,
+                                     unsigned long long* d_mismatches, cudaStream_t);
 cudaError_t launch_ffma_peak(float* out, int iters, int grid, int block, cudaStream_t);
 double      ffma_peak_flops_per_launch(int iters, int grid, int block);
 
@@ -53,7 +55,7 @@ struct DeviceContext {
     int          next_slot = 0;
     uint32_t*    d_out    = nullptr;   size_t d_out_cap = 0;     // internal frame buffer (pixels)
     unsigned char* h_stage = nullptr;  size_t h_stage_cap = 0;   // pinned staging for pageable destinations
-    std::map<std::pair<size_t, int>, int> occupancy;             // (hot_bytes, fast) -> CTAs per SM
+    std::map<std::pair<size_t, int>, std::pair<int, int>> occupancy;   // (hot_bytes, fast) -> (CTAs per SM, CTA width)
 };
 
 std::mutex                    g_mutex;          // one render at a time per process (lib.rs is single-threaded)
@@ -193,6 +195,8 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
 
     RtFrameParams P{};
     P.camera       = camera.d;
+    P.wm1          = (float)(W - 1u);      // `(width - 1) as f32`, common.rs:335
+    P.hm1          = (float)(H - 1u);
     P.width        = W;
     P.height       = H;
     P.spp          = opt.samples_per_pixel;
@@ -213,16 +217,22 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
     P.work_counter = &slot->work;
 
     // launch geometry: persistent CTAs, resident-CTA count from the occupancy API
-    const size_t hot_bytes  = (size_t)(scene.view.n_sph + scene.view.n_tri) * sizeof(RtFloat4);
+    const size_t hot_bytes  = (size_t)(scene.view.n_sph_pad + scene.view.n_tri) * sizeof(RtFloat4);
     const size_t smem_limit = ctx.smem_optin > 1024 ? ctx.smem_optin - 1024 : 0;   // static smem: the mbarrier
-    int&         per_sm     = ctx.occupancy[{hot_bytes, opt.fast_math ? 1 : 0}];
-    if (per_sm == 0) {
-        RT_CUDA(opt.fast_math ? occupancy_fast(hot_bytes, smem_limit, &per_sm)
-                              : occupancy_exact(hot_bytes, smem_limit, &per_sm));
-        if (per_sm < 1) throw std::runtime_error("render kernel does not fit on this device");
+    auto&        occ        = ctx.occupancy[{hot_bytes, opt.fast_math ? 1 : 0}];
+    if (occ.first == 0) {
+        RT_CUDA(opt.fast_math ? occupancy_fast(hot_bytes, smem_limit, &occ.first, &occ.second)
+                              : occupancy_exact(hot_bytes, smem_limit, &occ.first, &occ.second));
+        if (occ.first < 1) throw std::runtime_error("render kernel does not fit on this device");
     }
-    const uint64_t want_ctas = (slots + 255u) / 256u;
+    const int      per_sm = occ.first, block = occ.second;
+    const uint64_t want_ctas = (slots + (uint64_t)block - 1) / (uint64_t)block;
     int grid = (int)std::min<uint64_t>((uint64_t)per_sm * ctx.num_sms, std::max<uint64_t>(want_ctas, 1));
+    // Work-queue granularity: a warp takes `reserve` pixel slots per atomicAdd.  Aim for >= 64
+    // slabs per warp so that the last slab of the slowest warp is a small part of the frame.
+    const uint64_t warps   = (uint64_t)grid * (uint64_t)(block / 32);
+    uint64_t       reserve = slots / (warps * 64u) / 32u * 32u;
+    P.reserve = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(reserve, 32u), 256u);
 
     if (n_tiles > 0) {
         RT_CUDA(cudaMemsetAsync(slot, 0, sizeof(CounterSlot), stream));
@@ -279,6 +289,7 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
         RenderStats& st = *opt.stats;
         st = RenderStats{};
         st.grid       = (uint32_t)grid;
+        st.block      = (uint32_t)block;
         st.resident   = hot_bytes <= smem_limit ? 1u : 0u;
         st.smem_bytes = st.resident ? (uint32_t)hot_bytes : 0u;
         if (n_tiles > 0) {
@@ -347,6 +358,25 @@ double measure_fp32_peak_tflops(int device, float* sm_clock_mhz_out)
         *sm_clock_mhz_out = khz / 1000.0f;
     }
     return best;
+}
+
+long long selftest_division(int device, unsigned long long operand_sets, uint32_t seed)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    const int dev = resolve_device(device);
+    RT_CUDA(cudaSetDevice(dev));
+    DeviceContext& ctx = context_for(dev);
+    const int block = 256, grid = ctx.num_sms * 4;
+    const unsigned long long per_thread = (operand_sets + (unsigned long long)grid * block - 1) / ((unsigned long long)grid * block);
+    unsigned long long* d = nullptr;
+    RT_CUDA(cudaMalloc(&d, sizeof *d));
+    RT_CUDA(cudaMemsetAsync(d, 0, sizeof *d, ctx.stream));
+    RT_CUDA(launch_selftest_division(per_thread, seed, grid, block, d, ctx.stream));
+    unsigned long long h = 0;
+    RT_CUDA(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, ctx.stream));
+    RT_CUDA(cudaStreamSynchronize(ctx.stream));
+    RT_CUDA(cudaFree(d));
+    return (long long)h;
 }
 
 void* alloc_pinned(size_t bytes)

@@ -87,6 +87,8 @@ struct RenderStats {
     uint32_t grid       = 0;
     uint32_t smem_bytes = 0;
     uint32_t resident   = 0;     // 1: primitive list staged in shared memory
+    uint32_t block      = 0;     // threads per CTA
+    uint32_t reserved   = 0;
 };
 
 // common.rs:289-294, extended.  The reference fields keep their names.
@@ -125,8 +127,8 @@ struct World {
     // packed host copy of the scene blob (rt_types.h layout), built on demand
     struct Packed {
         std::vector<unsigned char> blob;
-        size_t off_sph = 0, off_tri_plane = 0, off_tri_v = 0, off_mat = 0, off_sph_r = 0, off_mat_type = 0;
-        uint32_t n_sph = 0, n_tri = 0;
+        size_t off_sph = 0, off_tri_plane = 0, off_tri_v = 0, off_info = 0;
+        uint32_t n_sph = 0, n_sph_pad = 0, n_tri = 0;
         RtSceneView view(const unsigned char* base) const;
     };
     const Packed& packed() const;
@@ -172,6 +174,9 @@ bool write_image_p6(const Framebuffer& fb, const char* path);
 int    device_count();
 // FFMA-chain microbenchmark: measured FP32 peak of `device` in TFLOP/s (FMA = 2 flops).
 double measure_fp32_peak_tflops(int device, float* sm_clock_mhz_out);
+// GPU self-test of the shared-reciprocal divide against the compiler's IEEE divide on
+// `operand_sets` pseudo-random operand sets; returns the number of mismatching sets.
+long long selftest_division(int device, unsigned long long operand_sets, uint32_t seed);
 // Pinned host allocations for callers that want the frame DMA'd straight into their buffer.
 void* alloc_pinned(size_t bytes);
 void  free_pinned(void* p);

@@ -4,15 +4,18 @@
 // One persistent launch per frame (or per progressive pass) replaces the reference's
 // row -> column -> sample -> bounce loop nest (common.rs:320-361):
 //
-//   * grid = (#SMs x resident CTAs per SM) CTAs of RT_BLOCK threads; every warp pulls work
-//     from one global counter in slabs of RT_RESERVE pixel slots, so the frame is balanced
-//     dynamically and no CTA wave tail exists.
+//   * grid = (#SMs x resident CTAs per SM) CTAs; every warp pulls work from one global
+//     counter in slabs of P.reserve pixel slots (sized by the host so that a warp takes
+//     dozens of slabs per frame), so the frame is balanced dynamically and there is neither a
+//     CTA wave tail nor a long last-slab tail.
 //   * one LANE owns one pixel at a time and adds that pixel's samples in order (float
 //     addition is not associative — this is what keeps the sums bit-identical to
 //     common.rs:338-340).  A lane whose path ends starts its next sample in the very next
 //     iteration, and a lane whose pixel is finished takes the next pixel slot (warp-level
 //     ballot/popc compaction of the slab) — no lane ever waits for its neighbours' longer
-//     paths.  Each loop iteration traces exactly one ray segment per live lane.
+//     paths.  Each loop iteration traces exactly one ray segment per live lane, and the
+//     expensive steps of that segment (normalisations, World::hit, random_unit_sphere) are
+//     shared by all lanes whatever their paths are doing (rt_trace.cuh, trace_segment).
 //   * the primitive list ({c, r*r} per sphere, {n, n.v0} per triangle — 16 B each) is staged
 //     once per CTA into shared memory with one TMA bulk copy (cp.async.bulk + mbarrier);
 //     every warp then reads it with broadcast LDS.128.  Scenes too large for shared memory
@@ -25,12 +28,6 @@
 
 #include <cuda_runtime.h>
 
-#ifndef RT_BLOCK
-#define RT_BLOCK 256
-#endif
-#ifndef RT_RESERVE
-#define RT_RESERVE 128u   // pixel slots a warp reserves per atomicAdd (multiple of 32)
-#endif
 
 namespace rt {
 
@@ -106,9 +103,13 @@ __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_
     return s;
 }
 
-template <bool FAST, bool SMEM>
-__global__ void __launch_bounds__(RT_BLOCK) rt_render_kernel(const __grid_constant__ RtFrameParams P,
-                                                            const __grid_constant__ RtSceneView  G)
+#ifndef RT_MIN_CTAS_SMALL
+#define RT_MIN_CTAS_SMALL 4   // 256-thread CTAs per SM the register allocation must allow (<= 64 registers)
+#endif
+
+template <bool FAST, bool SMEM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) rt_render_kernel(const __grid_constant__ RtFrameParams P,
+                                                         const __grid_constant__ RtSceneView  G)
 {
     extern __shared__ __align__(128) unsigned char rt_smem[];
     __shared__ __align__(8) unsigned long long rt_mbar;
@@ -116,10 +117,10 @@ __global__ void __launch_bounds__(RT_BLOCK) rt_render_kernel(const __grid_consta
     const RtFloat4* sph;
     const RtFloat4* tri_plane;
     if (SMEM) {
-        const uint32_t hot_bytes = (G.n_sph + G.n_tri) * (uint32_t)sizeof(RtFloat4);
+        const uint32_t hot_bytes = (G.n_sph_pad + G.n_tri) * (uint32_t)sizeof(RtFloat4);
         if (hot_bytes) stage_scene_tma(rt_smem, G.sph, hot_bytes, &rt_mbar);   // sph | tri_plane contiguous
         sph       = reinterpret_cast<const RtFloat4*>(rt_smem);
-        tri_plane = sph + G.n_sph;
+        tri_plane = sph + G.n_sph_pad;
     } else {
         sph       = G.sph;
         tri_plane = G.tri_plane;
@@ -138,87 +139,57 @@ __global__ void __launch_bounds__(RT_BLOCK) rt_render_kernel(const __grid_consta
     uint32_t pool_next = 0, pool_end = 0;
     bool     exhausted = false;
 
-    // per-lane pixel state
-    bool     have = false;
-    uint32_t column = 0, ref_row = 0, out_index = 0;
-    int32_t  sample = 0;
-    float    acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_a = 0.f;
-    Path     path;
-    path.seg_left = 0;
-    path.rng      = 1u;
-    path.o = path.d = path.thr = mk(0.f, 0.f, 0.f);
+    Lane L;
+    L.have = false;
+    L.fcol = L.frow = 0.f;
+    L.pix_hash = L.out_index = 0u;
+    L.sample = 0; L.seg_left = 0; L.rng = 1u; L.pend_unit = false;
+    L.acc_r = L.acc_g = L.acc_b = L.acc_a = 0.f;
+    L.o = L.pend = L.thr = mk(0.f, 0.f, 0.f);
     uint32_t segments = 0;
 
     for (;;) {
         // ---- 1. lanes without a pixel take the next slots of the warp's slab ----
-        uint32_t need = __ballot_sync(FULL, !have);
+        uint32_t need = __ballot_sync(FULL, !L.have);
         while (need && !exhausted) {
             if (pool_next == pool_end) {
                 uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(P.work_counter, RT_RESERVE);
+                if (lane == 0) base = atomicAdd(P.work_counter, P.reserve);
                 base = __shfl_sync(FULL, base, 0);
                 if (base >= total_slots) { exhausted = true; break; }
                 pool_next = base;
-                pool_end  = min(base + RT_RESERVE, total_slots);
+                pool_end  = min(base + P.reserve, total_slots);
             }
             const uint32_t avail = pool_end - pool_next;
             const uint32_t rank  = __popc(need & lt);
-            if (!have && rank < avail) {
+            if (!L.have && rank < avail) {
                 PixelSlot s = decode_slot(P, pool_next + rank, subtiles_x, chunks_per_strip);
                 if (s.valid) {
-                    column    = s.column;
-                    ref_row   = P.height - 1u - s.image_row;        // common.rs:351 (vertical flip)
-                    out_index = s.out_index;
-                    sample    = 0;
-                    path.seg_left = 0;
+                    begin_pixel(L, P, s.column, P.height - 1u - s.image_row, s.out_index);   // common.rs:351 (flip)
                     if (P.flags & RT_FLAG_ACCUM_IN) {
-                        RtFloat4 a = ld4(&P.accum[out_index]);
-                        acc_r = a.x; acc_g = a.y; acc_b = a.z; acc_a = a.w;
-                    } else {
-                        acc_r = acc_g = acc_b = 0.f; acc_a = 1.f;   // Color::new(0,0,0), common.rs:333
+                        RtFloat4 a = ld4(&P.accum[s.out_index]);
+                        L.acc_r = a.x; L.acc_g = a.y; L.acc_b = a.z; L.acc_a = a.w;
                     }
-                    have = true;
                 }
             }
             pool_next += min(avail, (uint32_t)__popc(need));
-            need = __ballot_sync(FULL, !have);
+            need = __ballot_sync(FULL, !L.have);
         }
-        if (__ballot_sync(FULL, have) == 0u) break;
+        if (__ballot_sync(FULL, L.have) == 0u) break;
 
-        bool finished_sample = false;
-        V3   colour = mk(0.f, 0.f, 0.f);
+        // ---- 2. one ray segment per live lane (sample start, World::hit, scatter, accumulate) ----
+        if (L.have && trace) segments += trace_segment<FAST>(L, P, G, sph, tri_plane);
 
-        if (have && trace) {
-            // ---- 2. start the next sample of this lane's pixel ----
-            if (path.seg_left == 0) start_sample<FAST>(path, P, column, ref_row, (uint32_t)(P.sample_begin + sample));
-
-            // ---- 3. one ray segment: World::hit + scatter ----
-            Hit h = closest_hit<FAST>(sph, G.n_sph, tri_plane, G.tri_v, G.n_tri, path.o, path.d);
-            ++segments;
-            if (shade<FAST>(G, sph, path, h, colour)) {
-                if (--path.seg_left == 0) { finished_sample = true; colour = mk(0.f, 0.f, 0.f); }   // common.rs:284
-            } else {
-                finished_sample = true;
+        // ---- 3. resolve + pack when the pixel is complete ----
+        if (L.have && (!trace || L.sample >= P.spp)) {
+            if (!trace && P.spp > 0) L.acc_a += (float)P.spp;   // depth <= 0: spp black samples, alpha 1 each
+            if (P.flags & RT_FLAG_ACCUM_OUT) {
+                float4 a = make_float4(L.acc_r, L.acc_g, L.acc_b, L.acc_a);
+                *reinterpret_cast<float4*>(&P.accum[L.out_index]) = a;
             }
-        }
-
-        // ---- 4. accumulate in sample order; resolve + pack when the pixel is complete ----
-        if (have) {
-            if (finished_sample) {
-                acc_r += colour.x; acc_g += colour.y; acc_b += colour.z; acc_a += 1.0f;   // add_with_alpha
-                path.seg_left = 0;
-                ++sample;
-            }
-            if (!trace || sample >= P.spp) {
-                if (!trace && P.spp > 0) acc_a += (float)P.spp;   // depth <= 0: spp black samples, alpha 1 each
-                if (P.flags & RT_FLAG_ACCUM_OUT) {
-                    float4 a = make_float4(acc_r, acc_g, acc_b, acc_a);
-                    *reinterpret_cast<float4*>(&P.accum[out_index]) = a;
-                }
-                if (!(P.flags & RT_FLAG_NO_RESOLVE))
-                    P.out[out_index] = resolve_pixel<FAST>(acc_r, acc_g, acc_b, acc_a, P.resolve_spp);
-                have = false;
-            }
+            if (!(P.flags & RT_FLAG_NO_RESOLVE))
+                P.out[L.out_index] = resolve_pixel<FAST>(L.acc_r, L.acc_g, L.acc_b, L.acc_a, P.resolve_spp);
+            L.have = false;
         }
     }
 
@@ -229,36 +200,65 @@ __global__ void __launch_bounds__(RT_BLOCK) rt_render_kernel(const __grid_consta
     if (lane == 0 && P.ray_counter && segs) atomicAdd(P.ray_counter, segs);
 }
 
+// Launch geometry.  Small primitive lists leave room for several 256-thread CTAs per SM;
+// a list that fills most of shared memory (thousands of primitives) allows only one CTA
+// per SM, which then has to be 1024 threads wide to keep the SM's schedulers fed.
+constexpr int    kBlockSmall    = 256;
+constexpr int    kBlockLarge    = 1024;
+constexpr size_t kLargeSmemFrom = 56 * 1024;   // above this, < 4 CTAs of 256 threads would fit
+
+inline int render_block_size(size_t hot_bytes, size_t smem_limit)
+{
+    return (hot_bytes > kLargeSmemFrom && hot_bytes <= smem_limit) ? kBlockLarge : kBlockSmall;
+}
+
+template <bool FAST, bool SMEM, int BLOCK>
+cudaError_t launch_one(const RtFrameParams& P, const RtSceneView& G, int grid, size_t smem_limit, size_t hot_bytes,
+                       cudaStream_t stream)
+{
+    auto k = rt_render_kernel<FAST, SMEM, BLOCK>;
+    if (SMEM) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+        if (e != cudaSuccess) return e;
+    }
+    k<<<grid, BLOCK, SMEM ? hot_bytes : 0, stream>>>(P, G);
+    return cudaGetLastError();
+}
+
 // Host-side launcher for one policy.
 template <bool FAST>
 cudaError_t launch_render(const RtFrameParams& P, const RtSceneView& G, int grid, size_t smem_limit,
                           cudaStream_t stream)
 {
-    const size_t hot_bytes = (size_t)(G.n_sph + G.n_tri) * sizeof(RtFloat4);
-    cudaError_t  e;
-    if (hot_bytes <= smem_limit) {
-        auto k = rt_render_kernel<FAST, true>;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
-        if (e != cudaSuccess) return e;
-        k<<<grid, RT_BLOCK, hot_bytes, stream>>>(P, G);
-    } else {
-        auto k = rt_render_kernel<FAST, false>;
-        k<<<grid, RT_BLOCK, 0, stream>>>(P, G);
-    }
-    return cudaGetLastError();
+    const size_t hot_bytes = (size_t)(G.n_sph_pad + G.n_tri) * sizeof(RtFloat4);
+    if (hot_bytes > smem_limit) return launch_one<FAST, false, kBlockSmall>(P, G, grid, smem_limit, hot_bytes, stream);
+    if (render_block_size(hot_bytes, smem_limit) == kBlockLarge)
+        return launch_one<FAST, true, kBlockLarge>(P, G, grid, smem_limit, hot_bytes, stream);
+    return launch_one<FAST, true, kBlockSmall>(P, G, grid, smem_limit, hot_bytes, stream);
 }
 
-template <bool FAST>
-cudaError_t render_occupancy(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm)
+template <bool FAST, bool SMEM, int BLOCK>
+cudaError_t occupancy_one(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm)
 {
-    if (hot_bytes <= smem_limit) {
-        auto k = rt_render_kernel<FAST, true>;
+    auto k = rt_render_kernel<FAST, SMEM, BLOCK>;
+    if (SMEM) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
         if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, RT_BLOCK, hot_bytes);
     }
-    auto k = rt_render_kernel<FAST, false>;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, RT_BLOCK, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, BLOCK, SMEM ? hot_bytes : 0);
+}
+
+// Resident CTAs per SM and the CTA width launch_render will use for this scene size.
+template <bool FAST>
+cudaError_t render_occupancy(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm, int* block_size)
+{
+    if (hot_bytes > smem_limit) {
+        *block_size = kBlockSmall;
+        return occupancy_one<FAST, false, kBlockSmall>(hot_bytes, smem_limit, blocks_per_sm);
+    }
+    *block_size = render_block_size(hot_bytes, smem_limit);
+    if (*block_size == kBlockLarge) return occupancy_one<FAST, true, kBlockLarge>(hot_bytes, smem_limit, blocks_per_sm);
+    return occupancy_one<FAST, true, kBlockSmall>(hot_bytes, smem_limit, blocks_per_sm);
 }
 
 }   // namespace rt

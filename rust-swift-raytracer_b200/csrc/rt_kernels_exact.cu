@@ -13,9 +13,64 @@ cudaError_t launch_render_exact(const RtFrameParams& P, const RtSceneView& G, in
     return launch_render<false>(P, G, grid, smem_limit, stream);
 }
 
-cudaError_t occupancy_exact(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm)
+cudaError_t occupancy_exact(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm, int* block_size)
 {
-    return render_occupancy<false>(hot_bytes, smem_limit, blocks_per_sm);
+    return render_occupancy<false>(hot_bytes, smem_limit, blocks_per_sm, block_size);
+}
+
+// ---- self-test of the shared-reciprocal divide (rt_trace.cuh, div3 / pixel_uv) -----------
+// Compares the hand-expanded sequence with the compiler's own IEEE `/` on pseudo-random
+// operands whose exponents sweep the whole guarded range and beyond (so the guard and the
+// fallback are exercised too).  Counts operand triples whose bits differ (NaN == NaN).
+__device__ __forceinline__ bool same_bits(float a, float b)
+{
+    return (__float_as_uint(a) == __float_as_uint(b)) || (a != a && b != b);
+}
+
+__global__ void rt_selftest_division_kernel(unsigned long long n_per_thread, uint32_t seed,
+                                            unsigned long long* mismatches)
+{
+    uint32_t rng = sample_seed(seed, blockIdx.x * blockDim.x + threadIdx.x, 0x5eedu);
+    unsigned long long bad = 0;
+    for (unsigned long long i = 0; i < n_per_thread; ++i) {
+        // random mantissas; exponents: mostly moderate, sometimes extreme / zero / denormal
+        uint32_t m[4], mode = xorshift32(rng);
+        for (int k = 0; k < 4; ++k) m[k] = xorshift32(rng);
+        float v[4];
+        for (int k = 0; k < 4; ++k) {
+            uint32_t bits = m[k];
+            uint32_t sel  = (mode >> (8 * k)) & 0xffu;
+            if (sel < 200u)      bits = (bits & 0x807fffffu) | ((117u + (bits >> 23) % 21u) << 23);   // 2^-10 .. 2^10
+            else if (sel < 240u) bits = (bits & 0x807fffffu) | ((47u + (bits >> 23) % 161u) << 23);   // 2^-80 .. 2^80
+            else if (sel < 250u) bits = bits;                                                          // anything (NaN, inf, denormal)
+            else                 bits = bits & 0x80000000u;                                            // +-0
+            v[k] = __uint_as_float(bits);
+        }
+        V3    a = mk(v[0], v[1], v[2]);
+        float b = fabsf(v[3]);
+        V3 q = div3<false>(a, b, false);
+        bad += !(same_bits(q.x, a.x / b) && same_bits(q.y, a.y / b) && same_bits(q.z, a.z / b));
+        // the normalisation use (|a.c| <= len by construction)
+        float len = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
+        V3 nq = div3<false>(a, len, true);
+        bad += !(same_bits(nq.x, a.x / len) && same_bits(nq.y, a.y / len) && same_bits(nq.z, a.z / len));
+        // pixel_uv: (column + xi) / (W - 1)
+        RtFrameParams P{};
+        P.wm1 = (float)((m[0] % 8191u) + ((mode & 1u) ? 0u : 1u));       // includes 0 (1-pixel frame)
+        P.hm1 = (float)((m[1] % 4095u) + 1u);
+        float au = (float)(m[2] % 8192u) + random_f32(rng), av = (float)(m[3] % 4096u) + random_f32(rng);
+        float u, w;
+        pixel_uv<false>(P, au, av, u, w);
+        bad += !(same_bits(u, au / P.wm1) && same_bits(w, av / P.hm1));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t launch_selftest_division(unsigned long long n_per_thread, uint32_t seed, int grid, int block,
+                                     unsigned long long* d_mismatches, cudaStream_t stream)
+{
+    rt_selftest_division_kernel<<<grid, block, 0, stream>>>(n_per_thread, seed, d_mismatches);
+    return cudaGetLastError();
 }
 
 }   // namespace rt

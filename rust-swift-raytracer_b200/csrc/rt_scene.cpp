@@ -126,17 +126,29 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 RtSceneView World::Packed::view(const unsigned char* base) const
 {
-    RtSceneView v;
+    RtSceneView v{};
     v.sph       = reinterpret_cast<const RtFloat4*>(base + off_sph);
     v.tri_plane = reinterpret_cast<const RtFloat4*>(base + off_tri_plane);
     v.tri_v     = reinterpret_cast<const RtFloat4*>(base + off_tri_v);
-    v.mat       = reinterpret_cast<const RtFloat4*>(base + off_mat);
-    v.sph_r     = reinterpret_cast<const float*>(base + off_sph_r);
-    v.mat_type  = reinterpret_cast<const uint32_t*>(base + off_mat_type);
+    v.info      = reinterpret_cast<const RtPrimInfo*>(base + off_info);
     v.n_sph     = n_sph;
+    v.n_sph_pad = n_sph_pad;
     v.n_tri     = n_tri;
     return v;
 }
+
+namespace {
+RtPrimInfo prim_info(const Material& m, float radius)
+{
+    RtPrimInfo i{};
+    i.r = m.r; i.g = m.g; i.b = m.b;
+    i.param     = m.param;
+    i.type      = (uint32_t)m.type;
+    i.inv_param = 1.0f / m.param;        // materials.rs:69 `1.0 / ir`, the same IEEE divide
+    i.radius    = radius;
+    return i;
+}
+}   // namespace
 
 // Scene pack: AoS {Sphere, Triangle} -> the SoA blob of rt_types.h.
 const World::Packed& World::packed() const
@@ -144,30 +156,29 @@ const World::Packed& World::packed() const
     if (packed_) return *packed_;
     auto p = std::make_unique<Packed>();
     const size_t S = spheres.size(), T = triangles.size(), P = S + T;
-    p->n_sph = (uint32_t)S;
-    p->n_tri = (uint32_t)T;
+    const size_t Sp = align_up(S, RT_SPHERE_GROUP);
+    p->n_sph     = (uint32_t)S;
+    p->n_sph_pad = (uint32_t)Sp;
+    p->n_tri     = (uint32_t)T;
     size_t off = 0;
-    p->off_sph       = off; off += S * sizeof(RtFloat4);
+    p->off_sph       = off; off += Sp * sizeof(RtFloat4);
     p->off_tri_plane = off; off += T * sizeof(RtFloat4);
     p->off_tri_v     = off; off += 3 * T * sizeof(RtFloat4);
-    p->off_mat       = off; off += P * sizeof(RtFloat4);
-    p->off_sph_r     = off; off += align_up(S * sizeof(float), 16);
-    p->off_mat_type  = off; off += align_up(P * sizeof(uint32_t), 16);
-    p->blob.assign(off ? off : 16, 0);
+    off = align_up(off, 32);
+    p->off_info      = off; off += P * sizeof(RtPrimInfo);
+    p->blob.assign(off ? off : 32, 0);
     unsigned char* base = p->blob.data();
     auto* sph   = reinterpret_cast<RtFloat4*>(base + p->off_sph);
     auto* plane = reinterpret_cast<RtFloat4*>(base + p->off_tri_plane);
     auto* triv  = reinterpret_cast<RtFloat4*>(base + p->off_tri_v);
-    auto* mat   = reinterpret_cast<RtFloat4*>(base + p->off_mat);
-    auto* sr    = reinterpret_cast<float*>(base + p->off_sph_r);
-    auto* mt    = reinterpret_cast<uint32_t*>(base + p->off_mat_type);
+    auto* info  = reinterpret_cast<RtPrimInfo*>(base + p->off_info);
     for (size_t i = 0; i < S; ++i) {
         const Sphere& s = spheres[i];
-        sph[i] = {s.center.x, s.center.y, s.center.z, s.radius * s.radius};   // radius.powi(2), common.rs:77
-        sr[i]  = s.radius;
-        mat[i] = {s.material.r, s.material.g, s.material.b, s.material.param};
-        mt[i]  = (uint32_t)s.material.type;
+        sph[i]  = {s.center.x, s.center.y, s.center.z, s.radius * s.radius};   // radius.powi(2), common.rs:77
+        info[i] = prim_info(s.material, s.radius);
     }
+    const float nan = std::nanf("");
+    for (size_t i = S; i < Sp; ++i) sph[i] = {nan, nan, nan, nan};            // padding: never hit
     for (size_t j = 0; j < T; ++j) {
         const Triangle& t = triangles[j];
         // common.rs:128-133,140: n = (v1-v0) x (v2-v0) and d = n.v0 depend on the triangle
@@ -177,8 +188,7 @@ const World::Packed& World::packed() const
         triv[3 * j + 0] = {t.v0.x, t.v0.y, t.v0.z, t.normal.x};
         triv[3 * j + 1] = {t.v1.x, t.v1.y, t.v1.z, t.normal.y};
         triv[3 * j + 2] = {t.v2.x, t.v2.y, t.v2.z, t.normal.z};
-        mat[S + j] = {t.material.r, t.material.g, t.material.b, t.material.param};
-        mt[S + j]  = (uint32_t)t.material.type;
+        info[S + j]     = prim_info(t.material, 1.0f);
     }
     packed_ = std::move(p);
     return *packed_;

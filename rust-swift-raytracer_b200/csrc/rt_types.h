@@ -3,12 +3,14 @@
 // Layout in HBM (one contiguous, 16-byte aligned "scene blob" per device, built once per
 // load_world / World::new and never touched by the render loop again):
 //
-//   [ sph       : float4 x S ]  {cx, cy, cz, r*r}      hot  — staged into shared memory
+//   [ sph       : float4 x Sp]  {cx, cy, cz, r*r}      hot  — staged into shared memory
 //   [ tri_plane : float4 x T ]  {n.x, n.y, n.z, n.v0}  hot  — staged into shared memory
 //   [ tri_v     : float4 x 3T]  {v_k.xyz, stored_normal[k]}   warm (plane-stage survivors)
-//   [ mat       : float4 x P ]  {r, g, b, fuzz|ir}     cold (one gather per hit), P = S+T
-//   [ sph_r     : float  x S ]  radius                 cold
-//   [ mat_type  : u32    x P ]  RT_MAT_*               cold
+//   [ info      : 32 B   x P ]  RtPrimInfo             cold (one gather per hit), P = S+T
+//
+// Sp = S rounded up to a multiple of RT_SPHERE_GROUP; the padding entries are all-NaN
+// spheres, which can never be hit (every comparison with NaN is false), so the closest-hit
+// loop runs in whole groups without a remainder loop.
 //
 // This is the SoA split the reference author sketches in raytracer/TODO.txt:27-39: the
 // closest-hit loop reads 16 B per primitive and nothing else.
@@ -36,16 +38,29 @@ struct RtCameraData {
 
 struct RtFloat4 { float x, y, z, w; };
 
+#define RT_SPHERE_GROUP 8u
+
+// Everything the shading step needs about the primitive that was hit: one 32-byte record,
+// fetched with two 16-byte loads.
+struct RtPrimInfo {
+    float    r, g, b;       // Color (alpha == 1)
+    float    param;         // Metal: fuzz, Dielectric: ir
+    uint32_t type;          // RT_MAT_*
+    float    inv_param;     // Dielectric: 1.0f / ir (materials.rs:69, evaluated once on the host)
+    float    radius;        // spheres: radius (common.rs:95 divides by it); triangles: 1
+    float    pad;
+};
+
 // Device- or host-resident view of a packed scene (pointers into the blob).
 struct RtSceneView {
-    const RtFloat4* sph;        // [S]
-    const RtFloat4* tri_plane;  // [T]
-    const RtFloat4* tri_v;      // [3T]
-    const RtFloat4* mat;        // [S+T]
-    const float*    sph_r;      // [S]
-    const uint32_t* mat_type;   // [S+T]
-    uint32_t        n_sph;
-    uint32_t        n_tri;
+    const RtFloat4*   sph;        // [n_sph_pad]
+    const RtFloat4*   tri_plane;  // [T]
+    const RtFloat4*   tri_v;      // [3T]
+    const RtPrimInfo* info;       // [S+T]
+    uint32_t          n_sph;
+    uint32_t          n_sph_pad;  // multiple of RT_SPHERE_GROUP
+    uint32_t          n_tri;
+    uint32_t          pad;
 };
 
 // Flags of RtFrameParams::flags
@@ -60,6 +75,7 @@ enum : uint32_t {
 // Everything one render launch needs (passed by value as a __grid_constant__).
 struct RtFrameParams {
     RtCameraData camera;
+    float    wm1, hm1;       // (W-1) as f32, (H-1) as f32: the divisors of common.rs:335-336
     uint32_t width, height;
     int32_t  spp;            // samples traced by this launch (common.rs:334)
     int32_t  depth;          // max_ray_bounces (common.rs:267)
@@ -70,6 +86,8 @@ struct RtFrameParams {
     // Row-tile sharding: this launch renders image-row tiles
     //   tile_first, tile_first + tile_stride, ...   (n_tiles of them, tile_rows rows each).
     uint32_t tile_rows, tile_first, tile_stride, n_tiles;
+    uint32_t reserve;        // pixel slots a warp takes per atomicAdd (multiple of 32)
+    uint32_t pad0;
     uint32_t* out;           // RGBA8 as u32, full frame or compact (RT_FLAG_COMPACT_OUT)
     RtFloat4* accum;         // optional float4 sums, same indexing as out
     unsigned long long* ray_counter;   // += number of World::hit calls

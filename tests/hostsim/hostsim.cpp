@@ -29,6 +29,7 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
     RtFrameParams P{};
     std::memcpy(&P.camera, cam12, sizeof(float) * 12);
     P.width = W; P.height = H; P.spp = spp; P.depth = depth; P.seed = seed; P.flags = flags;
+    P.wm1 = (float)(W - 1u); P.hm1 = (float)(H - 1u);
     P.sample_begin = sample_begin;
     P.resolve_spp  = resolve_spp ? resolve_spp : sample_begin + spp;
 
@@ -37,26 +38,12 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
     const bool trace = spp > 0 && depth > 0;
     for (uint32_t image_row = 0; image_row < H; ++image_row)
         for (uint32_t column = 0; column < W; ++column) {
-            const uint32_t ref_row = H - 1u - image_row;
-            float r = 0.f, g = 0.f, b = 0.f, a = 1.f;
-            if (trace) {
-                for (int32_t s = 0; s < spp; ++s) {
-                    Path path;
-                    start_sample<false>(path, P, column, ref_row, (uint32_t)(sample_begin + s));
-                    V3 colour = mk(0.f, 0.f, 0.f);
-                    for (;;) {
-                        Hit h = closest_hit<false>(G.sph, G.n_sph, G.tri_plane, G.tri_v, G.n_tri, path.o, path.d);
-                        ++rays;
-                        if (shade<false>(G, G.sph, path, h, colour)) {
-                            if (--path.seg_left == 0) { colour = mk(0.f, 0.f, 0.f); break; }
-                        } else break;
-                    }
-                    r += colour.x; g += colour.y; b += colour.z; a += 1.0f;
-                }
-            } else if (spp > 0) {
-                a += (float)spp;
-            }
-            out32[image_row * W + column] = resolve_pixel<false>(r, g, b, a, P.resolve_spp);
+            Lane L{};
+            begin_pixel(L, P, column, H - 1u - image_row, image_row * W + column);
+            // the kernel's loop for one lane: one ray segment per iteration until the pixel is complete
+            while (trace && L.sample < spp) rays += trace_segment<false>(L, P, G, G.sph, G.tri_plane);
+            if (!trace && spp > 0) L.acc_a += (float)spp;
+            out32[L.out_index] = resolve_pixel<false>(L.acc_r, L.acc_g, L.acc_b, L.acc_a, P.resolve_spp);
         }
     if (rays_out) *rays_out = rays;
     return 0;

@@ -151,6 +151,13 @@ def test_scene_too_large_for_shared_memory_uses_global_path(gpu_rt, ob, scenes):
     assert st.resident == 0 and st.rays == rays and np.array_equal(got, want)
 
 
+def test_shared_reciprocal_divide_equals_ieee_divide(gpu_rt):
+    """rt_trace.cuh div3 / pixel_uv: 3 x 2^29 operand sets (moderate, extreme, zero, denormal,
+    NaN/inf exponents), every quotient compared bit for bit with the compiler's `/`."""
+    for seed in (1, 2, 3):
+        assert gpu_rt.selftest_division(1 << 29, seed) == 0
+
+
 # ------------------------------------------------------------------ progressive, shards, device API
 
 def test_progressive_passes_equal_one_pass(gpu_rt, ob, scenes):
