@@ -93,6 +93,9 @@ int rt_set_camera_vertical_fov(struct Rust_WorldHandle *handle, const float orig
 int rt_set_camera_look_at(struct Rust_WorldHandle *handle, const float origin[3],
                           const float look_at[3], const float up[3],
                           float vertical_fov_radians, float aspect_ratio);
+/* Install a camera verbatim: origin, lower_left_corner, horizontal, vertical (camera.rs:8-15)
+ * as 12 floats — for callers that build the Camera with the crate's own constructors. */
+int rt_set_camera_raw(struct Rust_WorldHandle *handle, const float camera12[12]);
 /* origin, lower_left_corner, horizontal, vertical (camera.rs:8-15) as 12 floats. */
 void  rt_get_camera(const struct Rust_Camera *camera, float out12[12]);
 float rt_camera_aspect_ratio(const struct Rust_Camera *camera);   /* camera.rs:70-72 */

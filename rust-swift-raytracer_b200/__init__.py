@@ -82,7 +82,8 @@ EXPORTED_SYMBOLS = (
     "load_world", "render", "move_camera_position",
     "rt_last_error", "rt_abi_version", "rt_device_count", "rt_free_world", "rt_free_camera",
     "render_with_options", "rt_render_device", "rt_shard_pixel_count",
-    "rt_set_camera_at", "rt_set_camera_vertical_fov", "rt_set_camera_look_at", "rt_get_camera",
+    "rt_set_camera_at", "rt_set_camera_vertical_fov", "rt_set_camera_look_at", "rt_set_camera_raw",
+    "rt_get_camera",
     "rt_camera_aspect_ratio", "rt_world_new", "rt_world_add_sphere", "rt_world_add_triangle",
     "rt_world_sphere_count", "rt_world_triangle_count", "rt_world_get_sphere", "rt_world_get_triangle",
     "rt_write_image", "rt_write_image_p6",
@@ -127,6 +128,8 @@ def lib() -> C.CDLL:
     L.rt_set_camera_vertical_fov.argtypes = [hp, f3, C.c_float, C.c_float]
     L.rt_set_camera_look_at.restype = C.c_int
     L.rt_set_camera_look_at.argtypes = [hp, f3, f3, f3, C.c_float, C.c_float]
+    L.rt_set_camera_raw.restype = C.c_int
+    L.rt_set_camera_raw.argtypes = [hp, f3]
     L.rt_get_camera.restype = None
     L.rt_get_camera.argtypes = [C.c_void_p, f3]
     L.rt_camera_aspect_ratio.restype = C.c_float
@@ -292,6 +295,12 @@ class WorldHandle:
 
     def aspect_ratio(self) -> float:
         return lib().rt_camera_aspect_ratio(self.ptr.contents.camera)
+
+    def set_camera_raw(self, camera12):
+        """Install origin, lower_left_corner, horizontal, vertical (12 floats) verbatim."""
+        a = (C.c_float * 12)(*[float(x) for x in camera12])
+        if lib().rt_set_camera_raw(self.ptr, a):
+            raise RenderError(last_error())
 
     def set_camera_at(self, origin, aspect):
         if lib().rt_set_camera_at(self.ptr, _f3(origin), float(aspect)):

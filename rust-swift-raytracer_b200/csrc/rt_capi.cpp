@@ -194,6 +194,15 @@ int rt_set_camera_look_at(Rust_WorldHandle* h, const float origin[3], const floa
         replace_camera(h, c);
     });
 }
+int rt_set_camera_raw(Rust_WorldHandle* h, const float camera12[12])
+{
+    return guarded([&] {
+        if (!h || !camera12) throw std::runtime_error("NULL world handle or camera");
+        rt::Camera c;
+        std::memcpy(&c.d, camera12, 12 * sizeof(float));
+        replace_camera(h, c);
+    });
+}
 void rt_get_camera(const Rust_Camera* camera, float out12[12])
 {
     if (!camera) return;

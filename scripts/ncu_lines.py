@@ -15,5 +15,6 @@ tot = sum(int(r[ie]) for _, _, r in items); tots = sum(int(r[sm]) for _, _, r in
 print(f"files lines {len(items)}  warp-instr {tot:,}  samples {tots:,}")
 for f, d, r in items:
     if int(r[ie]) >= thr * tot or int(r[sm]) >= thr * tots:
-        thr_avg = float(r[at]) / max(1, 1)
-        print(f"{f:16s}:{r[0]:>4s} inst {int(r[ie])/tot*100:6.2f}%  smp {int(r[sm])/tots*100:6.2f}%  {r[1].strip()[:120]}")
+        ti = hdr.index("Thread Instructions Executed")
+        thr_avg = int(r[ti]) / max(int(r[ie]), 1)
+        print(f"{f:16s}:{r[0]:>4s} inst {int(r[ie])/tot*100:6.2f}%  smp {int(r[sm])/tots*100:6.2f}%  thr {thr_avg:5.1f}  {r[1].strip()[:110]}")

@@ -79,6 +79,13 @@ def test_camera_constructors_match_oracle(rt, ob, scenes):
         h.set_camera_look_at((0, 0, 0), (0, 1, 0), (0, 1, 0), 1.0, 1.0)     # camera.rs:62
 
 
+def test_set_camera_raw_round_trips(rt, scenes):
+    h = rt.load_world(scenes.default_world())
+    cam = np.arange(12, dtype=np.float32) * np.float32(0.37) - np.float32(1.5)
+    h.set_camera_raw(cam)
+    assert np.array_equal(h.camera_floats(), cam)
+
+
 def test_world_builder_reaches_emission(rt):
     h = rt.world_new((0, 0, 0), 1.5)
     h.add_sphere((0, 0, -1), 0.5, rt.EMISSION, (2.0, 1.0, 0.5))
