@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--fast-math", action="store_true", help="relaxed-arithmetic kernel (not bit-exact)")
+    ap.add_argument("--spp", type=int, default=None, help="override the workload's spp (profiling only: "
+                    "the line then says so in config.workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -239,6 +241,9 @@ def main():
 
     wl = WORKLOADS[args.workload]
     desc, key, W, H, spp, depth, passes = wl
+    if args.spp:
+        spp, passes = args.spp, 1
+        desc += f" [REDUCED to {spp} spp for profiling — not a bench line]"
     handle = rt.load_world(scene_text(scenes, key))
     S, T = handle.n_spheres, handle.n_triangles
     dev = torch.device("cuda", local_rank)

@@ -217,7 +217,7 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
     P.work_counter = &slot->work;
 
     // launch geometry: persistent CTAs, resident-CTA count from the occupancy API
-    const size_t hot_bytes  = (size_t)(scene.view.n_sph_pad + scene.view.n_tri) * sizeof(RtFloat4);
+    const size_t hot_bytes  = (size_t)(scene.view.n_sph_pad + scene.view.n_tri_pad) * sizeof(RtFloat4);
     const size_t smem_limit = ctx.smem_optin > 1024 ? ctx.smem_optin - 1024 : 0;   // static smem: the mbarrier
     auto&        occ        = ctx.occupancy[{hot_bytes, opt.fast_math ? 1 : 0}];
     if (occ.first == 0) {

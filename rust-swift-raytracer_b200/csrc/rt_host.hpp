@@ -128,7 +128,7 @@ struct World {
     struct Packed {
         std::vector<unsigned char> blob;
         size_t off_sph = 0, off_tri_plane = 0, off_tri_v = 0, off_info = 0;
-        uint32_t n_sph = 0, n_sph_pad = 0, n_tri = 0;
+        uint32_t n_sph = 0, n_sph_pad = 0, n_tri = 0, n_tri_pad = 0;
         RtSceneView view(const unsigned char* base) const;
     };
     const Packed& packed() const;

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) r
     const RtFloat4* sph;
     const RtFloat4* tri_plane;
     if (SMEM) {
-        const uint32_t hot_bytes = (G.n_sph_pad + G.n_tri) * (uint32_t)sizeof(RtFloat4);
+        const uint32_t hot_bytes = (G.n_sph_pad + G.n_tri_pad) * (uint32_t)sizeof(RtFloat4);
         if (hot_bytes) stage_scene_tma(rt_smem, G.sph, hot_bytes, &rt_mbar);   // sph | tri_plane contiguous
         sph       = reinterpret_cast<const RtFloat4*>(rt_smem);
         tri_plane = sph + G.n_sph_pad;
@@ -230,7 +230,7 @@ template <bool FAST>
 cudaError_t launch_render(const RtFrameParams& P, const RtSceneView& G, int grid, size_t smem_limit,
                           cudaStream_t stream)
 {
-    const size_t hot_bytes = (size_t)(G.n_sph_pad + G.n_tri) * sizeof(RtFloat4);
+    const size_t hot_bytes = (size_t)(G.n_sph_pad + G.n_tri_pad) * sizeof(RtFloat4);
     if (hot_bytes > smem_limit) return launch_one<FAST, false, kBlockSmall>(P, G, grid, smem_limit, hot_bytes, stream);
     if (render_block_size(hot_bytes, smem_limit) == kBlockLarge)
         return launch_one<FAST, true, kBlockLarge>(P, G, grid, smem_limit, hot_bytes, stream);

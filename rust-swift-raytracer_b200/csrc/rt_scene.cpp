@@ -134,6 +134,7 @@ RtSceneView World::Packed::view(const unsigned char* base) const
     v.n_sph     = n_sph;
     v.n_sph_pad = n_sph_pad;
     v.n_tri     = n_tri;
+    v.n_tri_pad = n_tri_pad;
     return v;
 }
 
@@ -159,10 +160,12 @@ const World::Packed& World::packed() const
     const size_t Sp = align_up(S, RT_SPHERE_GROUP);
     p->n_sph     = (uint32_t)S;
     p->n_sph_pad = (uint32_t)Sp;
+    const size_t Tp = align_up(T, RT_TRI_GROUP);
     p->n_tri     = (uint32_t)T;
+    p->n_tri_pad = (uint32_t)Tp;
     size_t off = 0;
     p->off_sph       = off; off += Sp * sizeof(RtFloat4);
-    p->off_tri_plane = off; off += T * sizeof(RtFloat4);
+    p->off_tri_plane = off; off += Tp * sizeof(RtFloat4);
     p->off_tri_v     = off; off += 3 * T * sizeof(RtFloat4);
     off = align_up(off, 32);
     p->off_info      = off; off += P * sizeof(RtPrimInfo);
@@ -179,6 +182,7 @@ const World::Packed& World::packed() const
     }
     const float nan = std::nanf("");
     for (size_t i = S; i < Sp; ++i) sph[i] = {nan, nan, nan, nan};            // padding: never hit
+    for (size_t j = T; j < Tp; ++j) plane[j] = {nan, nan, nan, nan};
     for (size_t j = 0; j < T; ++j) {
         const Triangle& t = triangles[j];
         // common.rs:128-133,140: n = (v1-v0) x (v2-v0) and d = n.v0 depend on the triangle

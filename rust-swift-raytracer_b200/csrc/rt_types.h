@@ -4,13 +4,13 @@
 // load_world / World::new and never touched by the render loop again):
 //
 //   [ sph       : float4 x Sp]  {cx, cy, cz, r*r}      hot  — staged into shared memory
-//   [ tri_plane : float4 x T ]  {n.x, n.y, n.z, n.v0}  hot  — staged into shared memory
+//   [ tri_plane : float4 x Tp]  {n.x, n.y, n.z, n.v0}  hot  — staged into shared memory
 //   [ tri_v     : float4 x 3T]  {v_k.xyz, stored_normal[k]}   warm (plane-stage survivors)
 //   [ info      : 32 B   x P ]  RtPrimInfo             cold (one gather per hit), P = S+T
 //
-// Sp = S rounded up to a multiple of RT_SPHERE_GROUP; the padding entries are all-NaN
-// spheres, which can never be hit (every comparison with NaN is false), so the closest-hit
-// loop runs in whole groups without a remainder loop.
+// Sp = S rounded up to a multiple of RT_SPHERE_GROUP, Tp = T rounded up to a multiple of
+// RT_TRI_GROUP; the padding entries are all-NaN, which can never be hit (every comparison
+// with NaN is false), so the closest-hit loops run in whole groups without remainder loops.
 //
 // This is the SoA split the reference author sketches in raytracer/TODO.txt:27-39: the
 // closest-hit loop reads 16 B per primitive and nothing else.
@@ -39,6 +39,7 @@ struct RtCameraData {
 struct RtFloat4 { float x, y, z, w; };
 
 #define RT_SPHERE_GROUP 8u
+#define RT_TRI_GROUP    2u
 
 // Everything the shading step needs about the primitive that was hit: one 32-byte record,
 // fetched with two 16-byte loads.
@@ -60,7 +61,7 @@ struct RtSceneView {
     uint32_t          n_sph;
     uint32_t          n_sph_pad;  // multiple of RT_SPHERE_GROUP
     uint32_t          n_tri;
-    uint32_t          pad;
+    uint32_t          n_tri_pad;  // multiple of RT_TRI_GROUP
 };
 
 // Flags of RtFrameParams::flags
