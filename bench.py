@@ -204,6 +204,9 @@ def main():
     ap.add_argument("--fast-math", action="store_true", help="relaxed-arithmetic kernel (not bit-exact)")
     ap.add_argument("--spp", type=int, default=None, help="override the workload's spp (profiling only: "
                     "the line then says so in config.workload)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = render kernels store their tiles into rank 0's frame over NVLink "
+                         "(CUDA IPC mapping); 'nccl' = compact buffers + one dist.gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -247,7 +250,7 @@ def main():
     handle = rt.load_world(scene_text(scenes, key))
     S, T = handle.n_spheres, handle.n_triangles
     dev = torch.device("cuda", local_rank)
-    renderer = multi.ShardedRenderer(rt, handle, W, H, rank, n_gpus, tile_rows=16, device=dev)
+    renderer = multi.ShardedRenderer(rt, handle, W, H, rank, n_gpus, tile_rows=16, device=dev, gather=args.gather)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -322,8 +325,9 @@ def main():
                # the scene blob is uploaded once by load_world (the reference's API has the same split)
                "d2h_bytes_per_step": W * H * 4,
                "api": "render_with_options (C ABI, pinned host framebuffer)" if (n_gpus == 1 and passes == 1)
-                      else "multi.ShardedRenderer.render(to_host=True): tile shards -> NCCL gather -> D2H on rank 0"}
+                      else f"multi.ShardedRenderer.render(to_host=True): tile shards -> {renderer.gather} gather -> D2H on rank 0"}
 
+    renderer.close()
     if rank != 0:
         if n_gpus > 1:
             dist.destroy_process_group()
@@ -338,7 +342,10 @@ def main():
         "scaling": "strong" if n_gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "spheres": S, "triangles": T, "rays_per_step": int(rays_frame),
                    "samples_per_step": samples, "kernel": "fast-math" if fast else "exact (bit-identical to the oracle)",
-                   "parallelism": f"row-tile shards x{n_gpus} + gather to rank 0" if n_gpus > 1 else "1 GPU",
+                   "parallelism": (f"row-tile shards x{n_gpus}, {renderer.gather} gather to rank 0 "
+                                   + ("(tiles stored by the render kernels into rank 0's frame over NVLink, CUDA IPC)"
+                                      if renderer.gather == "peer" else "(compact buffers + dist.gather)"))
+                   if n_gpus > 1 else "1 GPU",
                    "l2": "flushed between steps (256 MiB write, outside the CUDA events)",
                    "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3},
         "e2e": e2e,

@@ -21,6 +21,9 @@ extern "C" {
 #define RT_OPT_ACCUM_IN     0x4u  /* continue from device_accum (progressive pass) */
 #define RT_OPT_ACCUM_OUT    0x8u  /* store the float4 sums back to device_accum */
 #define RT_OPT_NO_RESOLVE   0x10u /* skip the RGBA8 pack (intermediate progressive pass) */
+#define RT_OPT_FULL_FRAME_OUT 0x20u /* rt_render_device with shard_count > 1: device_pixels / device_accum are
+                                       FULL width*height frames (e.g. another GPU's frame mapped through CUDA IPC
+                                       or peer access); this shard's tiles are stored at their frame offsets */
 
 /* materials.rs:7-12 */
 #define RT_MATERIAL_DIFFUSE    0u
@@ -38,6 +41,8 @@ typedef struct RtRenderStats {
   uint32_t smem_bytes;  /* primitive-list bytes staged per CTA */
   uint32_t resident;    /* 1: primitive list lives in shared memory */
   uint32_t block;       /* threads per CTA */
+  uint32_t devices;     /* GPUs that rendered this frame */
+  uint32_t peer_gather; /* 1: shards stored their tiles straight into device 0's frame (NVLink peer stores) */
   uint32_t reserved;
 } RtRenderStats;
 
@@ -54,7 +59,9 @@ typedef struct RtRenderOptions {
   uint32_t tile_rows;          /* row-tile height of the shard decomposition; 0 -> 16 */
   uint32_t shard_index;        /* this call renders tiles shard_index, +shard_count, ... */
   uint32_t shard_count;        /* 0 -> 1 */
-  uint32_t reserved;
+  uint32_t n_devices;          /* render_with_options only: > 1 -> this one process renders the frame on
+                                  devices 0..n-1 (row tiles d, d+N, ...; tiles are stored straight into
+                                  device 0's frame over NVLink).  0 -> environment RT_GPUS, else 1 */
   RtRenderStats *stats;        /* optional out */
 } RtRenderOptions;
 
@@ -122,6 +129,19 @@ int rt_write_image_p6(struct Rust_CFramebuffer framebuffer, const char *path);
 /* Pinned host frame buffers: render() DMA's straight into them. */
 struct Rust_ColorU8 *rt_alloc_pixels(size_t width, size_t height);
 void                 rt_free_pixels(struct Rust_ColorU8 *pixels);
+
+/* Multi-process frame gather without a collective: rank 0 allocates the frame with
+ * rt_device_alloc and exports it (CUDA IPC, 64-byte handle); every other rank opens it and
+ * passes the mapped pointer as `device_pixels` of rt_render_device with RT_OPT_FULL_FRAME_OUT,
+ * so its render kernel stores its tiles straight into rank 0's memory over NVLink.
+ * rt_copy_to_host enqueues the final D2H on `stream`.  Pointers are NULL / results non-zero on
+ * failure (rt_last_error). */
+void *rt_device_alloc(size_t bytes);
+void  rt_device_free(void *device_ptr);
+int   rt_ipc_export(const void *device_ptr, unsigned char handle_out[64]);
+void *rt_ipc_open(const unsigned char handle[64]);
+int   rt_ipc_close(void *mapped_ptr);
+int   rt_copy_to_host(void *host_dst, const void *device_src, size_t bytes, void *stream);
 
 /* FFMA-chain microbenchmark: measured FP32 peak of `device` in TFLOP/s (the roofline
  * denominator of the render kernel).  Negative on failure. */

@@ -34,6 +34,7 @@ OPT_FAST_MATH = 0x2
 OPT_ACCUM_IN = 0x4
 OPT_ACCUM_OUT = 0x8
 OPT_NO_RESOLVE = 0x10
+OPT_FULL_FRAME_OUT = 0x20
 DIFFUSE, METAL, DIELECTRIC, EMISSION = 0, 1, 2, 3   # materials.rs:7-12
 
 
@@ -61,7 +62,7 @@ class RenderStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("kernel_ms", C.c_float),
                 ("total_ms", C.c_float), ("launches", C.c_uint32), ("grid", C.c_uint32),
                 ("smem_bytes", C.c_uint32), ("resident", C.c_uint32), ("block", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("devices", C.c_uint32), ("peer_gather", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -72,7 +73,7 @@ class _RenderOptions(C.Structure):
                 ("max_ray_bounces", C.c_int32), ("seed", C.c_uint32), ("flags", C.c_uint32),
                 ("sample_begin", C.c_int32), ("resolve_spp", C.c_int32), ("device", C.c_int32),
                 ("tile_rows", C.c_uint32), ("shard_index", C.c_uint32), ("shard_count", C.c_uint32),
-                ("reserved", C.c_uint32), ("stats", C.POINTER(RenderStats))]
+                ("n_devices", C.c_uint32), ("stats", C.POINTER(RenderStats))]
 
 
 _lib: Optional[C.CDLL] = None
@@ -88,6 +89,7 @@ EXPORTED_SYMBOLS = (
     "rt_world_sphere_count", "rt_world_triangle_count", "rt_world_get_sphere", "rt_world_get_triangle",
     "rt_write_image", "rt_write_image_p6",
     "rt_alloc_pixels", "rt_free_pixels", "rt_measure_fp32_peak", "rt_selftest_division",
+    "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_copy_to_host",
 )
 
 
@@ -158,6 +160,18 @@ def lib() -> C.CDLL:
     L.rt_free_pixels.argtypes = [C.c_void_p]
     L.rt_measure_fp32_peak.restype = C.c_double
     L.rt_measure_fp32_peak.argtypes = [C.c_int]
+    L.rt_device_alloc.restype = C.c_void_p
+    L.rt_device_alloc.argtypes = [C.c_size_t]
+    L.rt_device_free.restype = None
+    L.rt_device_free.argtypes = [C.c_void_p]
+    L.rt_ipc_export.restype = C.c_int
+    L.rt_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
+    L.rt_ipc_open.restype = C.c_void_p
+    L.rt_ipc_open.argtypes = [C.c_char_p]
+    L.rt_ipc_close.restype = C.c_int
+    L.rt_ipc_close.argtypes = [C.c_void_p]
+    L.rt_copy_to_host.restype = C.c_int
+    L.rt_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.rt_selftest_division.restype = C.c_longlong
     L.rt_selftest_division.argtypes = [C.c_int, C.c_ulonglong, C.c_uint32]
     _lib = L
@@ -193,14 +207,17 @@ class Options:
     accum_in: bool = False
     accum_out: bool = False
     no_resolve: bool = False
+    full_frame_out: bool = False         # sharded, but the device buffers are full frames (peer / IPC mapped)
+    n_devices: int = 0                   # > 1: this process renders on devices 0..n-1 (render_with_options only)
 
     def _c(self, stats: Optional[RenderStats]) -> _RenderOptions:
         flags = ((OPT_FIXED_JITTER if self.fixed_jitter else 0) | (OPT_FAST_MATH if self.fast_math else 0) |
                  (OPT_ACCUM_IN if self.accum_in else 0) | (OPT_ACCUM_OUT if self.accum_out else 0) |
-                 (OPT_NO_RESOLVE if self.no_resolve else 0))
+                 (OPT_NO_RESOLVE if self.no_resolve else 0) | (OPT_FULL_FRAME_OUT if self.full_frame_out else 0))
         o = _RenderOptions(C.sizeof(_RenderOptions), int(self.samples_per_pixel), int(self.max_ray_bounces),
                            int(self.seed) & 0xFFFFFFFF, flags, int(self.sample_begin), int(self.resolve_spp),
-                           int(self.device), int(self.tile_rows), int(self.shard_index), int(self.shard_count), 0,
+                           int(self.device), int(self.tile_rows), int(self.shard_index), int(self.shard_count),
+                           int(self.n_devices),
                            C.pointer(stats) if stats is not None else None)
         return o
 
@@ -393,6 +410,41 @@ def measure_fp32_peak(device: int = -1) -> float:
     if v < 0:
         raise RenderError(last_error())
     return v
+
+
+def device_alloc(nbytes: int) -> int:
+    p = lib().rt_device_alloc(int(nbytes))
+    if not p:
+        raise RenderError(last_error())
+    return p
+
+
+def device_free(ptr: int) -> None:
+    lib().rt_device_free(C.c_void_p(ptr))
+
+
+def ipc_export(ptr: int) -> bytes:
+    buf = C.create_string_buffer(64)
+    if lib().rt_ipc_export(C.c_void_p(ptr), buf):
+        raise RenderError(last_error())
+    return buf.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    p = lib().rt_ipc_open(C.create_string_buffer(handle, 64))
+    if not p:
+        raise RenderError(last_error())
+    return p
+
+
+def ipc_close(ptr: int) -> None:
+    if lib().rt_ipc_close(C.c_void_p(ptr)):
+        raise RenderError(last_error())
+
+
+def copy_to_host(host_ptr: int, device_ptr: int, nbytes: int, stream: int = 0) -> None:
+    if lib().rt_copy_to_host(C.c_void_p(host_ptr), C.c_void_p(device_ptr), int(nbytes), C.c_void_p(stream or None)):
+        raise RenderError(last_error())
 
 
 def selftest_division(operand_sets: int = 1 << 28, seed: int = 1, device: int = -1) -> int:

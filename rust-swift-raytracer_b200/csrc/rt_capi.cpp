@@ -3,6 +3,7 @@
 #include "../../include/raytracer_b200.h"
 #include "rt_host.hpp"
 
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 #include <stdexcept>
@@ -19,6 +20,15 @@ thread_local std::string g_error;
 void set_error(const std::string& s) { g_error = s; }
 void clear_error() { g_error.clear(); }
 
+// RT_GPUS=N lets an unchanged caller of render() (GameView.swift, examples/c_raytracer.rs) use N GPUs.
+int env_devices()
+{
+    const char* e = std::getenv("RT_GPUS");
+    if (!e || !*e) return 0;
+    int n = std::atoi(e);
+    return n > 0 ? n : 0;
+}
+
 rt::Options to_options(const RtRenderOptions* o)
 {
     rt::Options r;
@@ -34,6 +44,8 @@ rt::Options to_options(const RtRenderOptions* o)
     r.accum_in          = (c.flags & RT_OPT_ACCUM_IN) != 0;
     r.accum_out         = (c.flags & RT_OPT_ACCUM_OUT) != 0;
     r.no_resolve        = (c.flags & RT_OPT_NO_RESOLVE) != 0;
+    r.full_frame_out    = (c.flags & RT_OPT_FULL_FRAME_OUT) != 0;
+    r.n_devices         = (int32_t)c.n_devices;
     r.sample_begin      = c.sample_begin;
     r.resolve_spp       = c.resolve_spp;
     r.device            = c.device;
@@ -47,7 +59,7 @@ void export_stats(const rt::RenderStats& s, RtRenderStats* out)
 {
     out->rays = s.rays; out->samples = s.samples; out->kernel_ms = s.kernel_ms; out->total_ms = s.total_ms;
     out->launches = s.launches; out->grid = s.grid; out->smem_bytes = s.smem_bytes; out->resident = s.resident;
-    out->block = s.block; out->reserved = 0;
+    out->block = s.block; out->devices = s.devices; out->peer_gather = s.peer_gather; out->reserved = 0;
 }
 
 template <class F>
@@ -122,8 +134,13 @@ Rust_CFramebuffer render_with_options(Rust_CFramebuffer fb, const Rust_WorldHand
         rt::RenderStats st;
         RtRenderStats*  out_stats = (options && options->struct_size >= sizeof(RtRenderOptions)) ? options->stats : nullptr;
         if (out_stats) o.stats = &st;
-        rt::ray_trace_into(*handle->world->world, handle->camera->camera, fb.width, fb.height, o,
-                           reinterpret_cast<rt::ColorU8*>(fb.pixels), nullptr, nullptr, nullptr);
+        const int n_dev = o.n_devices > 0 ? o.n_devices : env_devices();
+        if (n_dev > 1 && o.shard_count <= 1)
+            rt::ray_trace_multi(*handle->world->world, handle->camera->camera, fb.width, fb.height, o,
+                                reinterpret_cast<rt::ColorU8*>(fb.pixels), n_dev);
+        else
+            rt::ray_trace_into(*handle->world->world, handle->camera->camera, fb.width, fb.height, o,
+                               reinterpret_cast<rt::ColorU8*>(fb.pixels), nullptr, nullptr, nullptr);
         if (out_stats) export_stats(st, out_stats);
     });
     return fb;
@@ -286,6 +303,29 @@ Rust_ColorU8* rt_alloc_pixels(size_t width, size_t height)
     return static_cast<Rust_ColorU8*>(p);
 }
 void rt_free_pixels(Rust_ColorU8* pixels) { rt::free_pinned(pixels); }
+
+void* rt_device_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    guarded([&] { p = rt::device_alloc(bytes); });
+    return p;
+}
+void rt_device_free(void* p) { rt::device_free(p); }
+int  rt_ipc_export(const void* device_ptr, unsigned char handle_out[64])
+{
+    return guarded([&] { rt::ipc_export(device_ptr, handle_out); });
+}
+void* rt_ipc_open(const unsigned char handle[64])
+{
+    void* p = nullptr;
+    guarded([&] { p = rt::ipc_open(handle); });
+    return p;
+}
+int rt_ipc_close(void* p) { return guarded([&] { rt::ipc_close(p); }); }
+int rt_copy_to_host(void* host_dst, const void* device_src, size_t bytes, void* stream)
+{
+    return guarded([&] { rt::copy_to_host(host_dst, device_src, bytes, stream); });
+}
 
 double rt_measure_fp32_peak(int device)
 {

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace rt {
 
@@ -154,44 +155,49 @@ bool is_pinned_or_device_accessible(const void* p)
 
 }   // namespace
 
-void ray_trace_into(const World& world, const Camera& camera, size_t width, size_t height,
-                    const Options& opt, ColorU8* host_pixels, void* device_pixels, void* device_accum,
-                    void* user_stream)
-{
-    const auto t_begin = std::chrono::steady_clock::now();
-    std::lock_guard<std::mutex> lock(g_mutex);
+namespace {
 
+// One shard's launch, enqueued on `stream` of ctx's device (which must be current).
+struct ShardLaunch {
+    uint32_t     n_tiles = 0;
+    bool         compact = false;
+    size_t       out_pixels = 0;
+    int          grid = 0, block = 0;
+    size_t       hot_bytes = 0, smem_limit = 0;
+    CounterSlot* slot = nullptr;
+    uint32_t*    d_out = nullptr;
+};
+
+void validate(size_t width, size_t height, const Options& opt, const void* device_accum)
+{
     if (width < 1 || height < 1) throw std::runtime_error("framebuffer must be at least 1x1");
     if (width > 0x3fffffffu || height > 0x3fffffffu) throw std::runtime_error("framebuffer too large");
     if (opt.tile_rows < 4 || (opt.tile_rows & 3u)) throw std::runtime_error("tile_rows must be a positive multiple of 4");
     if (opt.shard_count < 1 || opt.shard_index >= opt.shard_count) throw std::runtime_error("bad shard index/count");
     if ((opt.accum_in || opt.accum_out) && !device_accum) throw std::runtime_error("accumulator requested but device_accum is null");
+}
 
-    const int dev = resolve_device(opt.device);
-    RT_CUDA(cudaSetDevice(dev));
-    DeviceContext&     ctx   = context_for(dev);
-    const DeviceScene& scene = device_scene(world, ctx);
-    cudaStream_t       stream = user_stream ? static_cast<cudaStream_t>(user_stream) : ctx.stream;
-
-    const uint32_t W = (uint32_t)width, H = (uint32_t)height;
-    const uint32_t n_tiles = shard_tile_count(H, opt.tile_rows, opt.shard_index, opt.shard_count);
-    const uint64_t slots   = (uint64_t)n_tiles * ((W + 7u) / 8u) * (opt.tile_rows / 4u) * 32u;
+ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Camera& camera, uint32_t W, uint32_t H,
+                          const Options& opt, uint32_t* d_out_in, void* device_accum, cudaStream_t stream, bool timed)
+{
+    ShardLaunch L;
+    L.n_tiles = shard_tile_count(H, opt.tile_rows, opt.shard_index, opt.shard_count);
+    const uint64_t slots = (uint64_t)L.n_tiles * ((W + 7u) / 8u) * (opt.tile_rows / 4u) * 32u;
     if (slots >= 0xffffff00ull) throw std::runtime_error("frame shard exceeds 2^32 pixel slots; use more shards");
-    const bool   compact    = opt.shard_count > 1;
-    const size_t out_pixels = compact ? (size_t)n_tiles * opt.tile_rows * W : (size_t)W * H;
+    L.compact    = opt.shard_count > 1 && !opt.full_frame_out;
+    L.out_pixels = L.compact ? (size_t)L.n_tiles * opt.tile_rows * W : (size_t)W * H;
 
-    uint32_t* d_out = static_cast<uint32_t*>(device_pixels);
-    if (!d_out && !opt.no_resolve) {
-        if (ctx.d_out_cap < out_pixels) {
+    L.d_out = d_out_in;
+    if (!L.d_out && !opt.no_resolve) {
+        if (ctx.d_out_cap < L.out_pixels) {
             if (ctx.d_out) RT_CUDA(cudaFree(ctx.d_out));
             ctx.d_out = nullptr; ctx.d_out_cap = 0;
-            RT_CUDA(cudaMalloc(&ctx.d_out, out_pixels * sizeof(uint32_t)));
-            ctx.d_out_cap = out_pixels;
+            RT_CUDA(cudaMalloc(&ctx.d_out, L.out_pixels * sizeof(uint32_t)));
+            ctx.d_out_cap = L.out_pixels;
         }
-        d_out = ctx.d_out;
+        L.d_out = ctx.d_out;
     }
-
-    CounterSlot* slot = ctx.d_slots + (ctx.next_slot++ % kCounterSlots);
+    L.slot = ctx.d_slots + (ctx.next_slot++ % kCounterSlots);
 
     RtFrameParams P{};
     P.camera       = camera.d;
@@ -206,81 +212,113 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
     P.seed         = opt.seed;
     P.flags        = (opt.fixed_jitter ? RT_FLAG_FIXED_JITTER : 0u) | (opt.accum_in ? RT_FLAG_ACCUM_IN : 0u) |
               (opt.accum_out ? RT_FLAG_ACCUM_OUT : 0u) | (opt.no_resolve ? RT_FLAG_NO_RESOLVE : 0u) |
-              (compact ? RT_FLAG_COMPACT_OUT : 0u);
+              (L.compact ? RT_FLAG_COMPACT_OUT : 0u);
     P.tile_rows    = opt.tile_rows;
     P.tile_first   = opt.shard_index;
     P.tile_stride  = opt.shard_count;
-    P.n_tiles      = n_tiles;
-    P.out          = d_out;
+    P.n_tiles      = L.n_tiles;
+    P.out          = L.d_out;
     P.accum        = static_cast<RtFloat4*>(device_accum);
-    P.ray_counter  = &slot->rays;
-    P.work_counter = &slot->work;
+    P.ray_counter  = &L.slot->rays;
+    P.work_counter = &L.slot->work;
 
     // launch geometry: persistent CTAs, resident-CTA count from the occupancy API
-    const size_t hot_bytes  = (size_t)(scene.view.n_sph_pad + scene.view.n_tri_pad) * sizeof(RtFloat4);
-    const size_t smem_limit = ctx.smem_optin > 1024 ? ctx.smem_optin - 1024 : 0;   // static smem: the mbarrier
-    auto&        occ        = ctx.occupancy[{hot_bytes, opt.fast_math ? 1 : 0}];
+    L.hot_bytes  = (size_t)(scene.view.n_sph_pad + scene.view.n_tri_pad) * sizeof(RtFloat4);
+    L.smem_limit = ctx.smem_optin > 1024 ? ctx.smem_optin - 1024 : 0;   // static smem: the mbarrier
+    auto& occ    = ctx.occupancy[{L.hot_bytes, opt.fast_math ? 1 : 0}];
     if (occ.first == 0) {
-        RT_CUDA(opt.fast_math ? occupancy_fast(hot_bytes, smem_limit, &occ.first, &occ.second)
-                              : occupancy_exact(hot_bytes, smem_limit, &occ.first, &occ.second));
+        RT_CUDA(opt.fast_math ? occupancy_fast(L.hot_bytes, L.smem_limit, &occ.first, &occ.second)
+                              : occupancy_exact(L.hot_bytes, L.smem_limit, &occ.first, &occ.second));
         if (occ.first < 1) throw std::runtime_error("render kernel does not fit on this device");
     }
-    const int      per_sm = occ.first, block = occ.second;
-    const uint64_t want_ctas = (slots + (uint64_t)block - 1) / (uint64_t)block;
-    int grid = (int)std::min<uint64_t>((uint64_t)per_sm * ctx.num_sms, std::max<uint64_t>(want_ctas, 1));
+    L.block = occ.second;
+    const uint64_t want_ctas = (slots + (uint64_t)L.block - 1) / (uint64_t)L.block;
+    L.grid = (int)std::min<uint64_t>((uint64_t)occ.first * ctx.num_sms, std::max<uint64_t>(want_ctas, 1));
     // Work-queue granularity: a warp takes `reserve` pixel slots per atomicAdd.  Aim for >= 64
     // slabs per warp so that the last slab of the slowest warp is a small part of the frame.
-    const uint64_t warps   = (uint64_t)grid * (uint64_t)(block / 32);
+    const uint64_t warps   = (uint64_t)L.grid * (uint64_t)(L.block / 32);
     uint64_t       reserve = slots / (warps * 64u) / 32u * 32u;
     P.reserve = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(reserve, 32u), 256u);
 
-    if (n_tiles > 0) {
-        RT_CUDA(cudaMemsetAsync(slot, 0, sizeof(CounterSlot), stream));
-        if (opt.stats) RT_CUDA(cudaEventRecord(ctx.ev0, stream));
-        RT_CUDA(opt.fast_math ? launch_render_fast(P, scene.view, grid, smem_limit, stream)
-                              : launch_render_exact(P, scene.view, grid, smem_limit, stream));
-        if (opt.stats) RT_CUDA(cudaEventRecord(ctx.ev1, stream));
+    if (L.n_tiles > 0) {
+        RT_CUDA(cudaMemsetAsync(L.slot, 0, sizeof(CounterSlot), stream));
+        if (timed) RT_CUDA(cudaEventRecord(ctx.ev0, stream));
+        RT_CUDA(opt.fast_math ? launch_render_fast(P, scene.view, L.grid, L.smem_limit, stream)
+                              : launch_render_exact(P, scene.view, L.grid, L.smem_limit, stream));
+        if (timed) RT_CUDA(cudaEventRecord(ctx.ev1, stream));
     }
+    return L;
+}
+
+uint64_t shard_pixels(uint32_t W, uint32_t H, const Options& opt, uint32_t n_tiles)
+{
+    uint64_t px = 0;
+    for (uint32_t j = 0; j < n_tiles; ++j) {
+        const uint64_t tile = (uint64_t)opt.shard_index + (uint64_t)j * opt.shard_count;
+        const uint64_t r0   = tile * opt.tile_rows;
+        const uint64_t r1   = std::min<uint64_t>(r0 + opt.tile_rows, H);
+        px += (r1 - r0) * W;
+    }
+    return px;
+}
+
+void ensure_stage(DeviceContext& ctx, size_t bytes)
+{
+    if (ctx.h_stage_cap >= bytes) return;
+    if (ctx.h_stage) RT_CUDA(cudaFreeHost(ctx.h_stage));
+    ctx.h_stage = nullptr; ctx.h_stage_cap = 0;
+    RT_CUDA(cudaMallocHost(&ctx.h_stage, bytes));
+    ctx.h_stage_cap = bytes;
+}
+
+}   // namespace
+
+void ray_trace_into(const World& world, const Camera& camera, size_t width, size_t height,
+                    const Options& opt, ColorU8* host_pixels, void* device_pixels, void* device_accum,
+                    void* user_stream)
+{
+    const auto t_begin = std::chrono::steady_clock::now();
+    std::lock_guard<std::mutex> lock(g_mutex);
+    validate(width, height, opt, device_accum);
+
+    const int dev = resolve_device(opt.device);
+    RT_CUDA(cudaSetDevice(dev));
+    DeviceContext&     ctx   = context_for(dev);
+    const DeviceScene& scene = device_scene(world, ctx);
+    cudaStream_t       stream = user_stream ? static_cast<cudaStream_t>(user_stream) : ctx.stream;
+
+    const uint32_t W = (uint32_t)width, H = (uint32_t)height;
+    const ShardLaunch L = enqueue_shard(ctx, scene, camera, W, H, opt, static_cast<uint32_t*>(device_pixels),
+                                        device_accum, stream, opt.stats != nullptr);
+    const uint32_t n_tiles = L.n_tiles;
+    uint32_t*      d_out   = L.d_out;
 
     if (host_pixels && !opt.no_resolve && n_tiles > 0) {
         // D2H of the finished RGBA8 rows.  Every tile is one contiguous byte range of the frame
         // (image.rs:27 row-major), so a shard copies tile by tile and a full frame in one piece.
-        const bool   direct = is_pinned_or_device_accessible(host_pixels);
+        const bool   direct  = is_pinned_or_device_accessible(host_pixels);
         const size_t tile_px = (size_t)opt.tile_rows * W;
-        auto copy_range = [&](size_t dst_px, size_t src_px, size_t count) {
-            if (direct) {
-                RT_CUDA(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(host_pixels) + dst_px, d_out + src_px,
-                                        count * 4, cudaMemcpyDeviceToHost, stream));
-            } else {
-                RT_CUDA(cudaMemcpyAsync(ctx.h_stage + src_px * 4, d_out + src_px, count * 4, cudaMemcpyDeviceToHost, stream));
-            }
-        };
-        if (!direct && ctx.h_stage_cap < out_pixels * 4) {
-            if (ctx.h_stage) RT_CUDA(cudaFreeHost(ctx.h_stage));
-            ctx.h_stage = nullptr; ctx.h_stage_cap = 0;
-            RT_CUDA(cudaMallocHost(&ctx.h_stage, out_pixels * 4));
-            ctx.h_stage_cap = out_pixels * 4;
-        }
-        if (!compact) {
-            copy_range(0, 0, (size_t)W * H);
-            RT_CUDA(cudaStreamSynchronize(stream));
-            if (!direct) std::memcpy(host_pixels, ctx.h_stage, (size_t)W * H * 4);
-        } else {
+        uint32_t*    host32  = reinterpret_cast<uint32_t*>(host_pixels);
+        if (!direct) ensure_stage(ctx, L.out_pixels * 4);
+        // (frame offset, device offset, count) of every contiguous piece this shard owns
+        auto for_each_piece = [&](auto&& f) {
+            if (opt.shard_count <= 1) { f((size_t)0, (size_t)0, (size_t)W * H); return; }
             for (uint32_t j = 0; j < n_tiles; ++j) {
                 const size_t tile  = (size_t)opt.shard_index + (size_t)j * opt.shard_count;
                 const size_t first = tile * tile_px;
                 const size_t count = std::min(tile_px, (size_t)W * H - first);
-                copy_range(first, (size_t)j * tile_px, count);
+                f(first, L.compact ? (size_t)j * tile_px : first, count);
             }
-            RT_CUDA(cudaStreamSynchronize(stream));
-            if (!direct)
-                for (uint32_t j = 0; j < n_tiles; ++j) {
-                    const size_t tile  = (size_t)opt.shard_index + (size_t)j * opt.shard_count;
-                    const size_t first = tile * tile_px;
-                    const size_t count = std::min(tile_px, (size_t)W * H - first);
-                    std::memcpy(reinterpret_cast<uint32_t*>(host_pixels) + first, ctx.h_stage + (size_t)j * tile_px * 4, count * 4);
-                }
-        }
+        };
+        for_each_piece([&](size_t frame_px, size_t dev_px, size_t count) {
+            void* dst = direct ? (void*)(host32 + frame_px) : (void*)(ctx.h_stage + dev_px * 4);
+            RT_CUDA(cudaMemcpyAsync(dst, d_out + dev_px, count * 4, cudaMemcpyDeviceToHost, stream));
+        });
+        RT_CUDA(cudaStreamSynchronize(stream));
+        if (!direct)
+            for_each_piece([&](size_t frame_px, size_t dev_px, size_t count) {
+                std::memcpy(host32 + frame_px, ctx.h_stage + dev_px * 4, count * 4);
+            });
     } else if (!user_stream) {
         RT_CUDA(cudaStreamSynchronize(stream));
     }
@@ -288,28 +326,151 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
     if (opt.stats) {
         RenderStats& st = *opt.stats;
         st = RenderStats{};
-        st.grid       = (uint32_t)grid;
-        st.block      = (uint32_t)block;
-        st.resident   = hot_bytes <= smem_limit ? 1u : 0u;
-        st.smem_bytes = st.resident ? (uint32_t)hot_bytes : 0u;
+        st.grid       = (uint32_t)L.grid;
+        st.block      = (uint32_t)L.block;
+        st.resident   = L.hot_bytes <= L.smem_limit ? 1u : 0u;
+        st.smem_bytes = st.resident ? (uint32_t)L.hot_bytes : 0u;
         if (n_tiles > 0) {
-            RT_CUDA(cudaMemcpyAsync(ctx.h_slot, slot, sizeof(CounterSlot), cudaMemcpyDeviceToHost, stream));
+            RT_CUDA(cudaMemcpyAsync(ctx.h_slot, L.slot, sizeof(CounterSlot), cudaMemcpyDeviceToHost, stream));
             RT_CUDA(cudaStreamSynchronize(stream));
             RT_CUDA(cudaEventElapsedTime(&st.kernel_ms, ctx.ev0, ctx.ev1));
             st.rays     = ctx.h_slot->rays;
             st.launches = 1;
-            // samples actually traced by this shard
-            uint64_t px = 0;
-            for (uint32_t j = 0; j < n_tiles; ++j) {
-                const uint64_t tile = (uint64_t)opt.shard_index + (uint64_t)j * opt.shard_count;
-                const uint64_t r0   = tile * opt.tile_rows;
-                const uint64_t r1   = std::min<uint64_t>(r0 + opt.tile_rows, H);
-                px += (r1 - r0) * W;
-            }
-            st.samples = (opt.samples_per_pixel > 0 && opt.max_ray_bounces > 0) ? px * (uint64_t)opt.samples_per_pixel : 0;
+            st.samples  = (opt.samples_per_pixel > 0 && opt.max_ray_bounces > 0)
+                              ? shard_pixels(W, H, opt, n_tiles) * (uint64_t)opt.samples_per_pixel : 0;
         }
         st.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     }
+}
+
+// One process, several GPUs (the shape the C-ABI callers have: GameView.swift and
+// examples/c_raytracer.rs are single processes).  Device d renders row tiles d, d+N, ... and
+// its kernel stores the finished RGBA8 pixels DIRECTLY into device 0's frame through a
+// peer mapping (NVLink/NVSwitch): the gather of SURVEY.md 8e is fused into the pack step, no
+// separate collective or copy exists.  Device 0 then sends the frame to the host once.
+// Without peer access the shards fall back to one D2H per tile from every device.
+void ray_trace_multi(const World& world, const Camera& camera, size_t width, size_t height, const Options& opt_in,
+                     ColorU8* host_pixels, int n_devices)
+{
+    const auto t_begin = std::chrono::steady_clock::now();
+    if (!host_pixels) throw std::runtime_error("ray_trace_multi: host_pixels is null");
+    if (opt_in.accum_in || opt_in.accum_out || opt_in.no_resolve)
+        throw std::runtime_error("ray_trace_multi: progressive passes are per-device (use rt_render_device)");
+    int avail = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&avail);
+        if (e != cudaSuccess || avail == 0)
+            throw std::runtime_error("no CUDA device available (this library has no CPU render path)");
+    }
+    const int N = std::min(n_devices, avail);
+    if (N <= 1) {
+        Options o = opt_in;
+        o.device = 0; o.shard_index = 0; o.shard_count = 1; o.full_frame_out = false;
+        ray_trace_into(world, camera, width, height, o, host_pixels, nullptr, nullptr, nullptr);
+        return;
+    }
+    std::unique_lock<std::mutex> lock(g_mutex);
+    Options base = opt_in;
+    base.shard_count = (uint32_t)N;
+    validate(width, height, base, nullptr);
+    const uint32_t W = (uint32_t)width, H = (uint32_t)height;
+
+    // contexts, scenes, peer access to device 0
+    std::vector<DeviceContext*> ctxs(N);
+    bool peer = true;
+    for (int d = 0; d < N; ++d) {
+        RT_CUDA(cudaSetDevice(d));
+        ctxs[d] = &context_for(d);
+        (void)device_scene(world, *ctxs[d]);
+        if (d > 0) {
+            int can = 0;
+            RT_CUDA(cudaDeviceCanAccessPeer(&can, d, 0));
+            if (can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(0, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) fail("cudaDeviceEnablePeerAccess", e);
+                cudaGetLastError();
+            } else {
+                peer = false;
+            }
+        }
+    }
+    DeviceContext& c0 = *ctxs[0];
+    RT_CUDA(cudaSetDevice(0));
+    if (c0.d_out_cap < (size_t)W * H) {
+        RT_CUDA(cudaStreamSynchronize(c0.stream));
+        if (c0.d_out) RT_CUDA(cudaFree(c0.d_out));
+        c0.d_out = nullptr; c0.d_out_cap = 0;
+        RT_CUDA(cudaMalloc(&c0.d_out, (size_t)W * H * sizeof(uint32_t)));
+        c0.d_out_cap = (size_t)W * H;
+    }
+
+    std::vector<ShardLaunch> launches(N);
+    const bool   direct  = is_pinned_or_device_accessible(host_pixels);
+    uint32_t*    host32  = reinterpret_cast<uint32_t*>(host_pixels);
+    const size_t tile_px = (size_t)base.tile_rows * W;
+    for (int d = 0; d < N; ++d) {
+        RT_CUDA(cudaSetDevice(d));
+        Options o = base;
+        o.device = d; o.shard_index = (uint32_t)d; o.full_frame_out = peer;
+        launches[d] = enqueue_shard(*ctxs[d], device_scene(world, *ctxs[d]), camera, W, H, o,
+                                    peer ? c0.d_out : nullptr, nullptr, ctxs[d]->stream, true);
+        if (!peer && launches[d].n_tiles > 0) {        // fallback gather: D2H tile by tile from every device
+            if (!direct) ensure_stage(*ctxs[d], launches[d].out_pixels * 4);
+            for (uint32_t j = 0; j < launches[d].n_tiles; ++j) {
+                const size_t first = ((size_t)d + (size_t)j * N) * tile_px;
+                const size_t count = std::min(tile_px, (size_t)W * H - first);
+                void* dst = direct ? (void*)(host32 + first) : (void*)(ctxs[d]->h_stage + (size_t)j * tile_px * 4);
+                RT_CUDA(cudaMemcpyAsync(dst, launches[d].d_out + (size_t)j * tile_px, count * 4, cudaMemcpyDeviceToHost,
+                                        ctxs[d]->stream));
+            }
+        }
+    }
+    // wait for every device; with peer stores the frame is then complete in device 0's memory
+    for (int d = N - 1; d >= 0; --d) {
+        RT_CUDA(cudaSetDevice(d));
+        RT_CUDA(cudaStreamSynchronize(ctxs[d]->stream));
+        if (!peer && !direct)
+            for (uint32_t j = 0; j < launches[d].n_tiles; ++j) {
+                const size_t first = ((size_t)d + (size_t)j * N) * tile_px;
+                const size_t count = std::min(tile_px, (size_t)W * H - first);
+                std::memcpy(host32 + first, ctxs[d]->h_stage + (size_t)j * tile_px * 4, count * 4);
+            }
+    }
+    if (peer) {                                        // device 0 is current here
+        void* dst = host32;
+        if (!direct) { ensure_stage(c0, (size_t)W * H * 4); dst = c0.h_stage; }
+        RT_CUDA(cudaMemcpyAsync(dst, c0.d_out, (size_t)W * H * 4, cudaMemcpyDeviceToHost, c0.stream));
+        RT_CUDA(cudaStreamSynchronize(c0.stream));
+        if (!direct) std::memcpy(host32, c0.h_stage, (size_t)W * H * 4);
+    }
+
+    if (opt_in.stats) {
+        RenderStats& st = *opt_in.stats;
+        st = RenderStats{};
+        st.grid = (uint32_t)launches[0].grid; st.block = (uint32_t)launches[0].block;
+        st.resident   = launches[0].hot_bytes <= launches[0].smem_limit ? 1u : 0u;
+        st.smem_bytes = st.resident ? (uint32_t)launches[0].hot_bytes : 0u;
+        st.devices    = (uint32_t)N;
+        st.peer_gather = peer ? 1u : 0u;
+        for (int d = 0; d < N; ++d) {
+            if (launches[d].n_tiles == 0) continue;
+            RT_CUDA(cudaSetDevice(d));
+            DeviceContext& c = *ctxs[d];
+            RT_CUDA(cudaMemcpyAsync(c.h_slot, launches[d].slot, sizeof(CounterSlot), cudaMemcpyDeviceToHost, c.stream));
+            RT_CUDA(cudaStreamSynchronize(c.stream));
+            float ms = 0.f;
+            RT_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
+            st.kernel_ms = std::max(st.kernel_ms, ms);          // devices run concurrently
+            st.rays += c.h_slot->rays;
+            st.launches += 1;
+            Options o = base; o.shard_index = (uint32_t)d;
+            if (base.samples_per_pixel > 0 && base.max_ray_bounces > 0)
+                st.samples += shard_pixels(W, H, o, launches[d].n_tiles) * (uint64_t)base.samples_per_pixel;
+        }
+        RT_CUDA(cudaSetDevice(0));
+        st.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    }
+    RT_CUDA(cudaSetDevice(0));
 }
 
 Framebuffer ray_trace(const World& world, const Camera& camera, Framebuffer framebuffer, Options& options)
@@ -377,6 +538,35 @@ long long selftest_division(int device, unsigned long long operand_sets, uint32_
     RT_CUDA(cudaStreamSynchronize(ctx.stream));
     RT_CUDA(cudaFree(d));
     return (long long)h;
+}
+
+// ---- device memory helpers for the multi-process peer-store gather (multi.py) ----
+void* device_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    RT_CUDA(cudaMalloc(&p, bytes));
+    return p;
+}
+void device_free(void* p) { if (p) cudaFree(p); }
+void ipc_export(const void* device_ptr, unsigned char handle_out[64])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    RT_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(device_ptr)));
+    std::memcpy(handle_out, &h, 64);
+}
+void* ipc_open(const unsigned char handle[64])
+{
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    RT_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    return p;
+}
+void ipc_close(void* p) { if (p) RT_CUDA(cudaIpcCloseMemHandle(p)); }
+void copy_to_host(void* host_dst, const void* device_src, size_t bytes, void* stream)
+{
+    RT_CUDA(cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
 }
 
 void* alloc_pinned(size_t bytes)

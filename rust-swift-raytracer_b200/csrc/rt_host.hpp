@@ -88,6 +88,8 @@ struct RenderStats {
     uint32_t smem_bytes = 0;
     uint32_t resident   = 0;     // 1: primitive list staged in shared memory
     uint32_t block      = 0;     // threads per CTA
+    uint32_t devices    = 1;     // GPUs that rendered this frame
+    uint32_t peer_gather = 0;    // 1: shards stored their tiles straight into device 0's frame (NVLink peer stores)
     uint32_t reserved   = 0;
 };
 
@@ -109,6 +111,9 @@ struct Options {
     bool     accum_in       = false;        // continue from the float4 accumulator (progressive)
     bool     accum_out      = false;        // write the float4 accumulator back
     bool     no_resolve     = false;        // skip the RGBA8 pack (intermediate pass)
+    bool     full_frame_out = false;        // sharded, but device_pixels/device_accum are FULL frames (e.g. a
+                                            // peer-mapped frame on another GPU): tiles land at their frame offset
+    int32_t  n_devices      = 0;            // > 1: one process drives devices 0..n-1 (ray_trace_multi)
     RenderStats* stats      = nullptr;
 };
 
@@ -163,6 +168,12 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
                     const Options& options, ColorU8* host_pixels, void* device_pixels,
                     void* device_accum, void* stream);
 
+// The same frame rendered by `n_devices` GPUs driven from this one process: device d renders
+// row tiles d, d+N, ... and stores them straight into device 0's frame over NVLink peer
+// mappings; device 0 sends the finished frame to host_pixels.
+void ray_trace_multi(const World& world, const Camera& camera, size_t width, size_t height,
+                     const Options& options, ColorU8* host_pixels, int n_devices);
+
 // Number of rows / pixels shard `index` of `count` owns for an image of `height` rows.
 uint32_t shard_tile_count(uint32_t height, uint32_t tile_rows, uint32_t index, uint32_t count);
 
@@ -177,6 +188,14 @@ double measure_fp32_peak_tflops(int device, float* sm_clock_mhz_out);
 // GPU self-test of the shared-reciprocal divide against the compiler's IEEE divide on
 // `operand_sets` pseudo-random operand sets; returns the number of mismatching sets.
 long long selftest_division(int device, unsigned long long operand_sets, uint32_t seed);
+// Device memory that can be mapped into other processes (CUDA IPC): rank 0 owns the frame,
+// the other ranks' kernels store their tiles into it.  All throw std::runtime_error on failure.
+void* device_alloc(size_t bytes);
+void  device_free(void* p);
+void  ipc_export(const void* device_ptr, unsigned char handle_out[64]);
+void* ipc_open(const unsigned char handle[64]);
+void  ipc_close(void* p);
+void  copy_to_host(void* host_dst, const void* device_src, size_t bytes, void* stream);
 // Pinned host allocations for callers that want the frame DMA'd straight into their buffer.
 void* alloc_pinned(size_t bytes);
 void  free_pinned(void* p);

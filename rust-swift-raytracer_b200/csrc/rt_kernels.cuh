@@ -86,9 +86,15 @@ struct PixelSlot {
 __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_t slot, uint32_t subtiles_x,
                                                  uint32_t chunks_per_strip)
 {
+    // Slots run from the BOTTOM of the frame upwards: rows near the ground carry the long
+    // paths, rows of sky end after one segment, so the expensive pixels are handed out first
+    // and the tail of the launch (when the queue is empty and lanes drain) is made of cheap
+    // ones.  Pure scheduling: every pixel is computed the same way wherever it is in the order.
     const uint32_t chunk = slot >> 5, in = slot & 31u;
-    const uint32_t strip = chunk / chunks_per_strip;
-    const uint32_t c     = chunk - strip * chunks_per_strip;
+    const uint32_t rs    = chunk / chunks_per_strip;
+    const uint32_t strip = P.n_tiles - 1u - rs;
+    const uint32_t rc    = chunk - rs * chunks_per_strip;
+    const uint32_t c     = chunks_per_strip - 1u - rc;
     const uint32_t sy    = c / subtiles_x;
     const uint32_t sx    = c - sy * subtiles_x;
     const uint32_t x     = sx * 8u + (in & 7u);

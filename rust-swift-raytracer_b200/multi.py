@@ -70,52 +70,108 @@ def gather_frame(local: torch.Tensor, width: int, height: int, tile_rows: int, r
 class ShardedRenderer:
     """One rank's share of a tile-sharded frame, device-resident.
 
-    Every rank renders tiles rank, rank+world, ... of the frame into its compact RGBA8 buffer —
-    optionally as several progressive passes through a float4 accumulator that never leaves the
-    GPU — and the finished tiles are gathered to rank 0 (the only collective).  All kernels and
-    the gather are enqueued on torch's current CUDA stream, so CUDA events recorded on that
-    stream bracket the whole step.
+    Every rank renders tiles rank, rank+world, ... of the frame — optionally as several
+    progressive passes through a float4 accumulator that never leaves the GPU — and the finished
+    RGBA8 tiles end up on rank 0.  Two gathers:
+
+      gather="peer" (default for world > 1): rank 0 owns the frame (rt_device_alloc) and exports
+          it through CUDA IPC; the other ranks map it and their render kernels STORE their tiles
+          straight into rank 0's memory over NVLink (RT_OPT_FULL_FRAME_OUT) — the gather is
+          fused into the pack step of the kernel.  A one-element all-reduce enqueued after the
+          kernels orders rank 0's read after everybody's stores; it carries no frame data.
+      gather="nccl": every rank packs its tiles into a compact buffer; one dist.gather to rank 0
+          and a permuting view reassemble the frame (also the gloo/CPU-testable path).
+
+    All kernels, the collective and the optional D2H are enqueued on torch's current CUDA
+    stream, so CUDA events recorded on that stream bracket the whole step.
     """
 
     def __init__(self, rt, handle, width: int, height: int, rank: int = 0, world: int = 1,
-                 tile_rows: int = 16, device=None):
+                 tile_rows: int = 16, device=None, gather: Optional[str] = None):
         self.rt, self.handle = rt, handle
         self.width, self.height, self.rank, self.world, self.tile_rows = width, height, rank, world, tile_rows
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        self.local = alloc_compact(width, height, tile_rows, world, self.device)
+        self.gather = gather or ("peer" if world > 1 else "nccl")
+        assert self.gather in ("peer", "nccl")
         self.accum: Optional[torch.Tensor] = None
-        j = padded_tiles_per_rank(height, tile_rows, world)
-        self.staging = (torch.empty((world, j * tile_rows * width), dtype=torch.int32, device=self.device)
-                        if (world > 1 and rank == 0) else None)
         self.host_frame = (torch.empty((height, width), dtype=torch.int32).pin_memory() if rank == 0 else None)
+        self.frame_ptr = 0        # peer mode: rank 0's frame (own allocation on rank 0, IPC mapping elsewhere)
+        self._owns_frame = False
+        if self.gather == "peer" and world > 1:
+            nbytes = width * height * 4
+            box = [None]
+            if rank == 0:
+                self.frame_ptr = rt.device_alloc(nbytes)
+                self._owns_frame = True
+                box[0] = rt.ipc_export(self.frame_ptr)
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                self.frame_ptr = rt.ipc_open(box[0])
+            self.token = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.local = None
+            self.staging = None
+        else:
+            self.gather = "nccl"
+            self.local = alloc_compact(width, height, tile_rows, world, self.device)
+            j = padded_tiles_per_rank(height, tile_rows, world)
+            self.staging = (torch.empty((world, j * tile_rows * width), dtype=torch.int32, device=self.device)
+                            if (world > 1 and rank == 0) else None)
+
+    def close(self):
+        if self.frame_ptr:
+            torch.cuda.synchronize(self.device)
+            if self._owns_frame:
+                if self.world > 1:
+                    dist.barrier()            # nobody may still be storing into the frame
+                self.rt.device_free(self.frame_ptr)
+            else:
+                self.rt.ipc_close(self.frame_ptr)
+                dist.barrier()
+            self.frame_ptr = 0
 
     def render(self, spp: int, depth: int, passes: int = 1, seed: Optional[int] = None, fast_math: bool = False,
                fixed_jitter: bool = False, to_host: bool = False, count_rays: bool = False):
-        """Returns (frame, rays): frame is the [H, W] int32 RGBA8 frame on rank 0 (device tensor, or
-        the pinned host tensor when to_host) and None elsewhere; rays is this rank's ray-segment
-        count when count_rays (that mode synchronises after every pass), else 0."""
+        """Returns (frame, rays).  frame: on rank 0 the [H, W] int32 RGBA8 frame — the pinned host
+        tensor when to_host, else a device tensor (nccl gather) or the raw device address of the
+        frame (peer gather); None on the other ranks.  rays: this rank's ray-segment count when
+        count_rays (that mode synchronises after every pass), else 0."""
         rt = self.rt
         assert passes >= 1 and spp % passes == 0, "spp must divide evenly into passes"
+        peer = self.gather == "peer"
         if passes > 1 and self.accum is None:
-            self.accum = torch.empty((self.local.numel(), 4), dtype=torch.float32, device=self.device)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+            n = self.width * self.height if peer else self.local.numel()
+            self.accum = torch.empty((n, 4), dtype=torch.float32, device=self.device)
+        tstream = torch.cuda.current_stream(self.device)
+        stream = tstream.cuda_stream
+        out_ptr = self.frame_ptr if peer else self.local.data_ptr()
         per, rays = spp // passes, 0
         for p in range(passes):
             last = p == passes - 1
             o = rt.Options(per, depth, sample_begin=p * per, resolve_spp=spp, fast_math=fast_math,
                            fixed_jitter=fixed_jitter, tile_rows=self.tile_rows, shard_index=self.rank,
-                           shard_count=self.world, accum_in=p > 0, accum_out=not last, no_resolve=not last)
+                           shard_count=self.world, accum_in=p > 0, accum_out=not last, no_resolve=not last,
+                           full_frame_out=peer)
             if seed is not None:
                 o.seed = seed
             st = rt.RenderStats() if count_rays else None
-            rt.render_device(self.handle, o, self.width, self.height, self.local.data_ptr(),
+            rt.render_device(self.handle, o, self.width, self.height, out_ptr,
                              self.accum.data_ptr() if self.accum is not None else 0, stream, st)
             if st is not None:
                 rays += st.rays
+        if peer:
+            # stream-ordered completion fence: rank 0's all-reduce kernel cannot finish before every
+            # rank has launched its own, i.e. before every rank's render kernels have completed
+            dist.all_reduce(self.token)
+            frame = self.frame_ptr if self.rank == 0 else None
+            if to_host and self.rank == 0:
+                rt.copy_to_host(self.host_frame.data_ptr(), self.frame_ptr, self.width * self.height * 4, stream)
+                tstream.synchronize()
+                frame = self.host_frame
+            return frame, rays
         frame = gather_frame(self.local, self.width, self.height, self.tile_rows, self.rank, self.world,
                              staging=self.staging)
         if to_host and frame is not None:
             self.host_frame.copy_(frame, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
+            tstream.synchronize()
             frame = self.host_frame
         return frame, rays

@@ -3,7 +3,7 @@
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "multi_gpu" > gpurun_out/pytest_multi.log 2>&1; tail -3 gpurun_out/pytest_multi.log
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "multi_gpu or many_gpus or per_gpu" > gpurun_out/pytest_multi.log 2>&1; tail -3 gpurun_out/pytest_multi.log
 python bench.py --workload c4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4_n1.json 2> gpurun_out/bench_c4_n1.err; cat gpurun_out/bench_c4_n1.json
 for n in 2 4 8; do
   if [ $n -le $N ]; then

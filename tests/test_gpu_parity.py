@@ -352,6 +352,80 @@ def test_c3_c5_reduced_spp_full_resolution_bands(gpu_rt, ob, scenes):
         assert st.resident == 1 and st.rays == rays and np.array_equal(got, want), key
 
 
+def test_one_process_many_gpus_peer_store_gather(gpu_rt, ob, scenes):
+    """render_with_options(n_devices=N): device d renders tiles d, d+N, ... and stores them
+    straight into device 0's frame (peer mapping); the frame equals the single-GPU frame."""
+    rt = gpu_rt
+    n = rt.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    W, H = 640, 360
+    h = rt.load_world(scenes.example_world())
+    full, st1 = _render(rt, h, W, H, 4, 8)
+    for nd in sorted({2, n}):
+        for pinned in (False, True):
+            got, st = _render(rt, h, W, H, 4, 8, pinned=pinned, n_devices=nd)
+            assert np.array_equal(got, full), (nd, pinned)
+            assert st.devices == nd and st.rays == st1.rays and st.launches == nd and st.peer_gather == 1
+
+
+def _dist_worker(rank, world, port, gather, q):
+    import importlib
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    rt = importlib.import_module("rust-swift-raytracer_b200")
+    multi = importlib.import_module("rust-swift-raytracer_b200.multi")
+    scenes = importlib.import_module("rust-swift-raytracer_b200.scenes")
+    h = rt.load_world(scenes.example_world())
+    W, H = 333, 170                                  # ragged: last tile is partial, tiles % world != 0
+    r = multi.ShardedRenderer(rt, h, W, H, rank, world, tile_rows=16, gather=gather)
+    frame, rays = r.render(8, 8, passes=2, to_host=True, count_rays=True)
+    frame2, _ = r.render(8, 8, passes=1, to_host=True)          # single pass == two progressive passes
+    t = torch.tensor([rays], dtype=torch.int64, device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        q.put((frame.numpy().copy(), frame2.numpy().copy(), int(t.item())))
+    r.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("gather", ["peer", "nccl"])
+def test_one_process_per_gpu_sharded_frame_equals_single_gpu(gpu_rt, scenes, gather):
+    """The bench's N > 1 path (one process per GPU, torch.distributed/NCCL): tile shards +
+    gather (peer stores through CUDA IPC, or dist.gather) == the single-GPU frame, bit for bit."""
+    import socket
+    import torch.multiprocessing as mp
+    rt = gpu_rt
+    if rt.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, gather, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    frame, frame2, rays = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    h = rt.load_world(scenes.example_world())
+    want, st = _render(rt, h, 333, 170, 8, 8)
+    assert rays == st.rays
+    assert np.array_equal(frame.view(np.uint8).reshape(170, 333, 4), want)
+    assert np.array_equal(frame2, frame)
+
+
 def test_multi_gpu_tile_gather_when_two_devices(gpu_rt, scenes):
     """Two devices in one process: device 1 renders its shard, the tiles land in the frame."""
     rt = gpu_rt
