@@ -26,7 +26,9 @@ from typing import Optional
 import numpy as np
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "lib" / "libraytracer.so"
+import os as _os
+_variant = _os.environ.get("RT_LIB_VARIANT", "")      # tuning experiments only (build.py)
+LIB_PATH = _HERE / ("lib_" + _variant if _variant else "lib") / "libraytracer.so"
 
 SEED_DEFAULT = 2547549            # random.rs:9
 OPT_FIXED_JITTER = 0x1

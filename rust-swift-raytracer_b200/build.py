@@ -16,7 +16,12 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-OUT_DIR = HERE / "lib"
+# Tuning experiments only: RT_BUILD_VARIANT=name builds lib_<name>/ with extra -D flags from
+# RT_BUILD_DEFINES ("A=1,B=2"); the package loads it when RT_LIB_VARIANT=name.  The shipped
+# library is always lib/libraytracer.so.
+_VARIANT = os.environ.get("RT_BUILD_VARIANT", "")
+_DEFINES = ["-D" + d for d in os.environ.get("RT_BUILD_DEFINES", "").split(",") if d]
+OUT_DIR = HERE / ("lib_" + _VARIANT if _VARIANT else "lib")
 OBJ_DIR = OUT_DIR / "obj"
 LIB = OUT_DIR / "libraytracer.so"
 
@@ -70,9 +75,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if not force and not _stale(o, [s] + hdrs):
             continue
         if comp == "nvcc":
-            cmd = [_nvcc(), "-ccbin", _cxx()] + ARCH + NVCC_COMMON + extra + ["-c", str(s), "-o", str(o)]
+            cmd = [_nvcc(), "-ccbin", _cxx()] + ARCH + NVCC_COMMON + extra + _DEFINES + ["-c", str(s), "-o", str(o)]
         else:
-            cmd = [_cxx()] + CXX_FLAGS + extra + ["-c", str(s), "-o", str(o)]
+            cmd = [_cxx()] + CXX_FLAGS + extra + _DEFINES + ["-c", str(s), "-o", str(o)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode:

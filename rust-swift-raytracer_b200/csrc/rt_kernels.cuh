@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) r
     L.fcol = L.frow = 0.f;
     L.pix_hash = L.out_index = 0u;
     L.sample = 0; L.seg_left = 0; L.rng = 1u; L.pend_unit = false;
-    L.acc_r = L.acc_g = L.acc_b = L.acc_a = 0.f;
+    L.acc_r = L.acc_g = L.acc_b = 0.f;
     L.o = L.pend = L.thr = mk(0.f, 0.f, 0.f);
     uint32_t segments = 0;
 
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) r
                     begin_pixel(L, P, s.column, P.height - 1u - s.image_row, s.out_index);   // common.rs:351 (flip)
                     if (P.flags & RT_FLAG_ACCUM_IN) {
                         RtFloat4 a = ld4(&P.accum[s.out_index]);
-                        L.acc_r = a.x; L.acc_g = a.y; L.acc_b = a.z; L.acc_a = a.w;
+                        L.acc_r = a.x; L.acc_g = a.y; L.acc_b = a.z;      // a.w is re-read at the end
                     }
                 }
             }
@@ -188,13 +188,15 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) r
 
         // ---- 3. resolve + pack when the pixel is complete ----
         if (L.have && (!trace || L.sample >= P.spp)) {
-            if (!trace && P.spp > 0) L.acc_a += (float)P.spp;   // depth <= 0: spp black samples, alpha 1 each
+            // alpha: 1.0 (or the accumulator's) + one per sample; depth <= 0 still adds spp black samples
+            const float a0    = (P.flags & RT_FLAG_ACCUM_IN) ? P.accum[L.out_index].w : 1.0f;
+            const float acc_a = pixel_alpha(a0, P.spp > 0 ? P.spp : 0);
             if (P.flags & RT_FLAG_ACCUM_OUT) {
-                float4 a = make_float4(L.acc_r, L.acc_g, L.acc_b, L.acc_a);
+                float4 a = make_float4(L.acc_r, L.acc_g, L.acc_b, acc_a);
                 *reinterpret_cast<float4*>(&P.accum[L.out_index]) = a;
             }
             if (!(P.flags & RT_FLAG_NO_RESOLVE))
-                P.out[L.out_index] = resolve_pixel<FAST>(L.acc_r, L.acc_g, L.acc_b, L.acc_a, P.resolve_spp);
+                P.out[L.out_index] = resolve_pixel<FAST>(L.acc_r, L.acc_g, L.acc_b, acc_a, P.resolve_spp);
             L.have = false;
         }
     }

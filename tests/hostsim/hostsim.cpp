@@ -42,8 +42,8 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
             begin_pixel(L, P, column, H - 1u - image_row, image_row * W + column);
             // the kernel's loop for one lane: one ray segment per iteration until the pixel is complete
             while (trace && L.sample < spp) rays += trace_segment<false>(L, P, G, G.sph, G.tri_plane);
-            if (!trace && spp > 0) L.acc_a += (float)spp;
-            out32[L.out_index] = resolve_pixel<false>(L.acc_r, L.acc_g, L.acc_b, L.acc_a, P.resolve_spp);
+            out32[L.out_index] = resolve_pixel<false>(L.acc_r, L.acc_g, L.acc_b, pixel_alpha(1.0f, spp > 0 ? spp : 0),
+                                                      P.resolve_spp);
         }
     if (rays_out) *rays_out = rays;
     return 0;
