@@ -43,7 +43,7 @@ typedef struct RtRenderStats {
   uint32_t block;       /* threads per CTA */
   uint32_t devices;     /* GPUs that rendered this frame */
   uint32_t peer_gather; /* 1: shards stored their tiles straight into device 0's frame (NVLink peer stores) */
-  uint32_t reserved;
+  uint32_t filtered;    /* 1: the exact kernel put its conservative FMA filter in front of the sphere tests */
 } RtRenderStats;
 
 /* common.rs:289-294 `Options`, extended.  Zero-initialise, then set struct_size. */

@@ -64,7 +64,7 @@ class RenderStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("kernel_ms", C.c_float),
                 ("total_ms", C.c_float), ("launches", C.c_uint32), ("grid", C.c_uint32),
                 ("smem_bytes", C.c_uint32), ("resident", C.c_uint32), ("block", C.c_uint32),
-                ("devices", C.c_uint32), ("peer_gather", C.c_uint32), ("reserved", C.c_uint32)]
+                ("devices", C.c_uint32), ("peer_gather", C.c_uint32), ("filtered", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

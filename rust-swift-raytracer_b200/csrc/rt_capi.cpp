@@ -59,7 +59,7 @@ void export_stats(const rt::RenderStats& s, RtRenderStats* out)
 {
     out->rays = s.rays; out->samples = s.samples; out->kernel_ms = s.kernel_ms; out->total_ms = s.total_ms;
     out->launches = s.launches; out->grid = s.grid; out->smem_bytes = s.smem_bytes; out->resident = s.resident;
-    out->block = s.block; out->devices = s.devices; out->peer_gather = s.peer_gather; out->reserved = 0;
+    out->block = s.block; out->devices = s.devices; out->peer_gather = s.peer_gather; out->filtered = s.filtered;
 }
 
 template <class F>

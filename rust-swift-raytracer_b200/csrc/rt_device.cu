@@ -15,6 +15,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace rt {
@@ -22,8 +23,10 @@ namespace rt {
 // defined in rt_kernels_exact.cu / rt_kernels_fast.cu
 cudaError_t launch_render_exact(const RtFrameParams&, const RtSceneView&, int grid, size_t smem_limit, cudaStream_t);
 cudaError_t launch_render_fast(const RtFrameParams&, const RtSceneView&, int grid, size_t smem_limit, cudaStream_t);
-cudaError_t occupancy_exact(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm, int* block_size);
-cudaError_t occupancy_fast(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm, int* block_size);
+cudaError_t occupancy_exact(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
+                            size_t* hot_bytes, int* resident, int* filtered);
+cudaError_t occupancy_fast(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
+                           size_t* hot_bytes, int* resident, int* filtered);
 cudaError_t launch_selftest_division(unsigned long long n_per_thread, uint32_t seed, int grid, int block,
                                      unsigned long long* d_mismatches, cudaStream_t);
 cudaError_t launch_ffma_peak(float* out, int iters, int grid, int block, cudaStream_t);
@@ -56,7 +59,8 @@ struct DeviceContext {
     int          next_slot = 0;
     uint32_t*    d_out    = nullptr;   size_t d_out_cap = 0;     // internal frame buffer (pixels)
     unsigned char* h_stage = nullptr;  size_t h_stage_cap = 0;   // pinned staging for pageable destinations
-    std::map<std::pair<size_t, int>, std::pair<int, int>> occupancy;   // (hot_bytes, fast) -> (CTAs per SM, CTA width)
+    struct Geometry { int per_sm = 0, block = 0, resident = 0, filtered = 0; size_t hot_bytes = 0; };
+    std::map<std::tuple<uint32_t, uint32_t, int>, Geometry> occupancy;   // (Sp, Tp, fast) -> launch geometry
 };
 
 std::mutex                    g_mutex;          // one render at a time per process (lib.rs is single-threaded)
@@ -164,6 +168,7 @@ struct ShardLaunch {
     size_t       out_pixels = 0;
     int          grid = 0, block = 0;
     size_t       hot_bytes = 0, smem_limit = 0;
+    bool         resident = false, filtered = false;
     CounterSlot* slot = nullptr;
     uint32_t*    d_out = nullptr;
 };
@@ -223,17 +228,21 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     P.work_counter = &L.slot->work;
 
     // launch geometry: persistent CTAs, resident-CTA count from the occupancy API
-    L.hot_bytes  = (size_t)(scene.view.n_sph_pad + scene.view.n_tri_pad) * sizeof(RtFloat4);
     L.smem_limit = ctx.smem_optin > 1024 ? ctx.smem_optin - 1024 : 0;   // static smem: the mbarrier
-    auto& occ    = ctx.occupancy[{L.hot_bytes, opt.fast_math ? 1 : 0}];
-    if (occ.first == 0) {
-        RT_CUDA(opt.fast_math ? occupancy_fast(L.hot_bytes, L.smem_limit, &occ.first, &occ.second)
-                              : occupancy_exact(L.hot_bytes, L.smem_limit, &occ.first, &occ.second));
-        if (occ.first < 1) throw std::runtime_error("render kernel does not fit on this device");
+    auto& occ    = ctx.occupancy[{scene.view.n_sph_pad, scene.view.n_tri_pad, opt.fast_math ? 1 : 0}];
+    if (occ.per_sm == 0) {
+        RT_CUDA(opt.fast_math ? occupancy_fast(scene.view, L.smem_limit, &occ.per_sm, &occ.block, &occ.hot_bytes,
+                                               &occ.resident, &occ.filtered)
+                              : occupancy_exact(scene.view, L.smem_limit, &occ.per_sm, &occ.block, &occ.hot_bytes,
+                                                &occ.resident, &occ.filtered));
+        if (occ.per_sm < 1) throw std::runtime_error("render kernel does not fit on this device");
     }
-    L.block = occ.second;
+    L.hot_bytes = occ.hot_bytes;
+    L.resident  = occ.resident != 0;
+    L.filtered  = occ.filtered != 0;
+    L.block = occ.block;
     const uint64_t want_ctas = (slots + (uint64_t)L.block - 1) / (uint64_t)L.block;
-    L.grid = (int)std::min<uint64_t>((uint64_t)occ.first * ctx.num_sms, std::max<uint64_t>(want_ctas, 1));
+    L.grid = (int)std::min<uint64_t>((uint64_t)occ.per_sm * ctx.num_sms, std::max<uint64_t>(want_ctas, 1));
     // Work-queue granularity: a warp takes `reserve` pixel slots per atomicAdd.  Aim for >= 64
     // slabs per warp so that the last slab of the slowest warp is a small part of the frame.
     const uint64_t warps   = (uint64_t)L.grid * (uint64_t)(L.block / 32);
@@ -328,8 +337,9 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
         st = RenderStats{};
         st.grid       = (uint32_t)L.grid;
         st.block      = (uint32_t)L.block;
-        st.resident   = L.hot_bytes <= L.smem_limit ? 1u : 0u;
+        st.resident   = L.resident ? 1u : 0u;
         st.smem_bytes = st.resident ? (uint32_t)L.hot_bytes : 0u;
+        st.filtered   = L.filtered ? 1u : 0u;
         if (n_tiles > 0) {
             RT_CUDA(cudaMemcpyAsync(ctx.h_slot, L.slot, sizeof(CounterSlot), cudaMemcpyDeviceToHost, stream));
             RT_CUDA(cudaStreamSynchronize(stream));
@@ -448,8 +458,9 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
         RenderStats& st = *opt_in.stats;
         st = RenderStats{};
         st.grid = (uint32_t)launches[0].grid; st.block = (uint32_t)launches[0].block;
-        st.resident   = launches[0].hot_bytes <= launches[0].smem_limit ? 1u : 0u;
+        st.resident   = launches[0].resident ? 1u : 0u;
         st.smem_bytes = st.resident ? (uint32_t)launches[0].hot_bytes : 0u;
+        st.filtered   = launches[0].filtered ? 1u : 0u;
         st.devices    = (uint32_t)N;
         st.peer_gather = peer ? 1u : 0u;
         for (int d = 0; d < N; ++d) {

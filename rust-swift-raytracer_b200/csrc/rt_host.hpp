@@ -90,7 +90,7 @@ struct RenderStats {
     uint32_t block      = 0;     // threads per CTA
     uint32_t devices    = 1;     // GPUs that rendered this frame
     uint32_t peer_gather = 0;    // 1: shards stored their tiles straight into device 0's frame (NVLink peer stores)
-    uint32_t reserved   = 0;
+    uint32_t filtered   = 0;     // 1: exact kernel ran its conservative sphere filter (large sphere lists)
 };
 
 // common.rs:289-294, extended.  The reference fields keep their names.
@@ -132,7 +132,7 @@ struct World {
     // packed host copy of the scene blob (rt_types.h layout), built on demand
     struct Packed {
         std::vector<unsigned char> blob;
-        size_t off_sph = 0, off_tri_plane = 0, off_tri_v = 0, off_info = 0;
+        size_t off_sph = 0, off_tri_plane = 0, off_sph_filter = 0, off_sph_r2 = 0, off_tri_v = 0, off_info = 0;
         uint32_t n_sph = 0, n_sph_pad = 0, n_tri = 0, n_tri_pad = 0;
         RtSceneView view(const unsigned char* base) const;
     };

@@ -31,6 +31,14 @@
 
 namespace rt {
 
+// bytes of the hot lists a CTA stages (block A or block B of rt_types.h)
+__host__ __device__ inline uint32_t rt_hot_bytes(const RtSceneView& G, bool filter)
+{
+    uint32_t b = (G.n_sph_pad + G.n_tri_pad) * (uint32_t)sizeof(RtFloat4);
+    if (filter) b += ((G.n_sph_pad * (uint32_t)sizeof(float)) + 15u) & ~15u;
+    return b;
+}
+
 // --- TMA bulk copy (global -> shared) of the hot primitive list -------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
@@ -113,23 +121,28 @@ __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_
 #define RT_MIN_CTAS_SMALL 4   // 256-thread CTAs per SM the register allocation must allow (<= 64 registers)
 #endif
 
-template <bool FAST, bool SMEM, int BLOCK>
+template <bool FAST, bool SMEM, int BLOCK, bool FILTER>
 __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) rt_render_kernel(const __grid_constant__ RtFrameParams P,
                                                          const __grid_constant__ RtSceneView  G)
 {
     extern __shared__ __align__(128) unsigned char rt_smem[];
     __shared__ __align__(8) unsigned long long rt_mbar;
 
+    // the hot lists: block A {sph | tri_plane}, or block B {sph_filter | tri_plane | sph_r2} (rt_types.h),
+    // each one contiguous range of the scene blob
     const RtFloat4* sph;
     const RtFloat4* tri_plane;
+    const float*    sph_r2 = nullptr;
     if (SMEM) {
-        const uint32_t hot_bytes = (G.n_sph_pad + G.n_tri_pad) * (uint32_t)sizeof(RtFloat4);
-        if (hot_bytes) stage_scene_tma(rt_smem, G.sph, hot_bytes, &rt_mbar);   // sph | tri_plane contiguous
+        const uint32_t hot_bytes = rt_hot_bytes(G, FILTER);
+        if (hot_bytes) stage_scene_tma(rt_smem, FILTER ? G.sph_filter : G.sph, hot_bytes, &rt_mbar);
         sph       = reinterpret_cast<const RtFloat4*>(rt_smem);
         tri_plane = sph + G.n_sph_pad;
+        if (FILTER) sph_r2 = reinterpret_cast<const float*>(tri_plane + G.n_tri_pad);
     } else {
-        sph       = G.sph;
+        sph       = FILTER ? G.sph_filter : G.sph;
         tri_plane = G.tri_plane;
+        if (FILTER) sph_r2 = G.sph_r2;
     }
 
     const uint32_t FULL = 0xffffffffu;
@@ -184,7 +197,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) r
         if (__ballot_sync(FULL, L.have) == 0u) break;
 
         // ---- 2. one ray segment per live lane (sample start, World::hit, scatter, accumulate) ----
-        if (L.have && trace) segments += trace_segment<FAST>(L, P, G, sph, tri_plane);
+        if (L.have && trace) segments += trace_segment<FAST, FILTER>(L, P, G, sph, sph_r2, tri_plane);
 
         // ---- 3. resolve + pack when the pixel is complete ----
         if (L.have && (!trace || L.sample >= P.spp)) {
@@ -211,26 +224,41 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) r
 // Launch geometry.  Small primitive lists leave room for several 256-thread CTAs per SM;
 // a list that fills most of shared memory (thousands of primitives) allows only one CTA
 // per SM, which then has to be 1024 threads wide to keep the SM's schedulers fed.
-constexpr int    kBlockSmall    = 256;
-constexpr int    kBlockLarge    = 1024;
-constexpr size_t kLargeSmemFrom = 56 * 1024;   // above this, < 4 CTAs of 256 threads would fit
+constexpr int      kBlockSmall    = 256;
+constexpr int      kBlockLarge    = 1024;
+constexpr size_t   kLargeSmemFrom = 56 * 1024;   // above this, < 4 CTAs of 256 threads would fit
+constexpr uint32_t kFilterFrom    = 64;          // spheres from which the exact kernel filters first
 
-inline int render_block_size(size_t hot_bytes, size_t smem_limit)
+struct RenderVariant { bool smem; int block; bool filter; size_t hot_bytes; };
+
+template <bool FAST>
+inline RenderVariant choose_variant(const RtSceneView& G, size_t smem_limit)
 {
-    return (hot_bytes > kLargeSmemFrom && hot_bytes <= smem_limit) ? kBlockLarge : kBlockSmall;
+    RenderVariant v;
+    v.filter    = !FAST && G.n_sph_pad >= kFilterFrom;
+    v.hot_bytes = rt_hot_bytes(G, v.filter);
+    v.smem      = v.hot_bytes <= smem_limit;
+    v.block     = (v.smem && v.hot_bytes > kLargeSmemFrom) ? kBlockLarge : kBlockSmall;
+    return v;
 }
 
-template <bool FAST, bool SMEM, int BLOCK>
-cudaError_t launch_one(const RtFrameParams& P, const RtSceneView& G, int grid, size_t smem_limit, size_t hot_bytes,
-                       cudaStream_t stream)
+// f(kernel pointer, block) for the variant's instantiation
+template <bool FAST, class F>
+cudaError_t with_kernel(const RenderVariant& v, F&& f)
 {
-    auto k = rt_render_kernel<FAST, SMEM, BLOCK>;
-    if (SMEM) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
-        if (e != cudaSuccess) return e;
+    if (FAST) {
+        if (!v.smem) return f(rt_render_kernel<FAST, false, kBlockSmall, false>, kBlockSmall);
+        if (v.block == kBlockLarge) return f(rt_render_kernel<FAST, true, kBlockLarge, false>, kBlockLarge);
+        return f(rt_render_kernel<FAST, true, kBlockSmall, false>, kBlockSmall);
     }
-    k<<<grid, BLOCK, SMEM ? hot_bytes : 0, stream>>>(P, G);
-    return cudaGetLastError();
+    constexpr bool X = !FAST;   // FILTER variants exist for the exact policy only
+    if (!v.smem) return v.filter ? f(rt_render_kernel<FAST, false, kBlockSmall, X>, kBlockSmall)
+                                 : f(rt_render_kernel<FAST, false, kBlockSmall, false>, kBlockSmall);
+    if (v.block == kBlockLarge)
+        return v.filter ? f(rt_render_kernel<FAST, true, kBlockLarge, X>, kBlockLarge)
+                        : f(rt_render_kernel<FAST, true, kBlockLarge, false>, kBlockLarge);
+    return v.filter ? f(rt_render_kernel<FAST, true, kBlockSmall, X>, kBlockSmall)
+                    : f(rt_render_kernel<FAST, true, kBlockSmall, false>, kBlockSmall);
 }
 
 // Host-side launcher for one policy.
@@ -238,35 +266,31 @@ template <bool FAST>
 cudaError_t launch_render(const RtFrameParams& P, const RtSceneView& G, int grid, size_t smem_limit,
                           cudaStream_t stream)
 {
-    const size_t hot_bytes = (size_t)(G.n_sph_pad + G.n_tri_pad) * sizeof(RtFloat4);
-    if (hot_bytes > smem_limit) return launch_one<FAST, false, kBlockSmall>(P, G, grid, smem_limit, hot_bytes, stream);
-    if (render_block_size(hot_bytes, smem_limit) == kBlockLarge)
-        return launch_one<FAST, true, kBlockLarge>(P, G, grid, smem_limit, hot_bytes, stream);
-    return launch_one<FAST, true, kBlockSmall>(P, G, grid, smem_limit, hot_bytes, stream);
+    const RenderVariant v = choose_variant<FAST>(G, smem_limit);
+    return with_kernel<FAST>(v, [&](auto k, int block) -> cudaError_t {
+        if (v.smem) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+            if (e != cudaSuccess) return e;
+        }
+        k<<<grid, block, v.smem ? v.hot_bytes : 0, stream>>>(P, G);
+        return cudaGetLastError();
+    });
 }
 
-template <bool FAST, bool SMEM, int BLOCK>
-cudaError_t occupancy_one(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm)
-{
-    auto k = rt_render_kernel<FAST, SMEM, BLOCK>;
-    if (SMEM) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
-        if (e != cudaSuccess) return e;
-    }
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, BLOCK, SMEM ? hot_bytes : 0);
-}
-
-// Resident CTAs per SM and the CTA width launch_render will use for this scene size.
+// Resident CTAs per SM, the CTA width and the staged bytes launch_render will use for this scene.
 template <bool FAST>
-cudaError_t render_occupancy(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm, int* block_size)
+cudaError_t render_occupancy(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
+                             size_t* hot_bytes, int* resident, int* filtered)
 {
-    if (hot_bytes > smem_limit) {
-        *block_size = kBlockSmall;
-        return occupancy_one<FAST, false, kBlockSmall>(hot_bytes, smem_limit, blocks_per_sm);
-    }
-    *block_size = render_block_size(hot_bytes, smem_limit);
-    if (*block_size == kBlockLarge) return occupancy_one<FAST, true, kBlockLarge>(hot_bytes, smem_limit, blocks_per_sm);
-    return occupancy_one<FAST, true, kBlockSmall>(hot_bytes, smem_limit, blocks_per_sm);
+    const RenderVariant v = choose_variant<FAST>(G, smem_limit);
+    *block_size = v.block; *hot_bytes = v.hot_bytes; *resident = v.smem ? 1 : 0; *filtered = v.filter ? 1 : 0;
+    return with_kernel<FAST>(v, [&](auto k, int block) -> cudaError_t {
+        if (v.smem) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k, block, v.smem ? v.hot_bytes : 0);
+    });
 }
 
 }   // namespace rt

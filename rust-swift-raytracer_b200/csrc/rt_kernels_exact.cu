@@ -13,9 +13,10 @@ cudaError_t launch_render_exact(const RtFrameParams& P, const RtSceneView& G, in
     return launch_render<false>(P, G, grid, smem_limit, stream);
 }
 
-cudaError_t occupancy_exact(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm, int* block_size)
+cudaError_t occupancy_exact(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
+                            size_t* hot_bytes, int* resident, int* filtered)
 {
-    return render_occupancy<false>(hot_bytes, smem_limit, blocks_per_sm, block_size);
+    return render_occupancy<false>(G, smem_limit, blocks_per_sm, block_size, hot_bytes, resident, filtered);
 }
 
 // ---- self-test of the shared-reciprocal divide (rt_trace.cuh, div3 / pixel_uv) -----------

@@ -12,9 +12,10 @@ cudaError_t launch_render_fast(const RtFrameParams& P, const RtSceneView& G, int
     return launch_render<true>(P, G, grid, smem_limit, stream);
 }
 
-cudaError_t occupancy_fast(size_t hot_bytes, size_t smem_limit, int* blocks_per_sm, int* block_size)
+cudaError_t occupancy_fast(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
+                            size_t* hot_bytes, int* resident, int* filtered)
 {
-    return render_occupancy<true>(hot_bytes, smem_limit, blocks_per_sm, block_size);
+    return render_occupancy<true>(G, smem_limit, blocks_per_sm, block_size, hot_bytes, resident, filtered);
 }
 
 // ---- FP32 peak microbenchmark: 16 independent FFMA chains per thread -------------------

@@ -129,6 +129,8 @@ RtSceneView World::Packed::view(const unsigned char* base) const
     RtSceneView v{};
     v.sph       = reinterpret_cast<const RtFloat4*>(base + off_sph);
     v.tri_plane = reinterpret_cast<const RtFloat4*>(base + off_tri_plane);
+    v.sph_filter = reinterpret_cast<const RtFloat4*>(base + off_sph_filter);
+    v.sph_r2     = reinterpret_cast<const float*>(base + off_sph_r2);
     v.tri_v     = reinterpret_cast<const RtFloat4*>(base + off_tri_v);
     v.info      = reinterpret_cast<const RtPrimInfo*>(base + off_info);
     v.n_sph     = n_sph;
@@ -166,6 +168,9 @@ const World::Packed& World::packed() const
     size_t off = 0;
     p->off_sph       = off; off += Sp * sizeof(RtFloat4);
     p->off_tri_plane = off; off += Tp * sizeof(RtFloat4);
+    p->off_sph_filter = off; off += Sp * sizeof(RtFloat4);
+    const size_t off_plane_b = off; off += Tp * sizeof(RtFloat4);
+    p->off_sph_r2    = off; off += align_up(Sp * sizeof(float), 16);
     p->off_tri_v     = off; off += 3 * T * sizeof(RtFloat4);
     off = align_up(off, 32);
     p->off_info      = off; off += P * sizeof(RtPrimInfo);
@@ -183,6 +188,14 @@ const World::Packed& World::packed() const
     const float nan = std::nanf("");
     for (size_t i = S; i < Sp; ++i) sph[i] = {nan, nan, nan, nan};            // padding: never hit
     for (size_t j = T; j < Tp; ++j) plane[j] = {nan, nan, nan, nan};
+    // block B: the conservative filter list of the exact kernel (rt_trace.cuh, sphere_filter_group)
+    auto* sphf = reinterpret_cast<RtFloat4*>(base + p->off_sph_filter);
+    auto* r2   = reinterpret_cast<float*>(base + p->off_sph_r2);
+    for (size_t i = 0; i < Sp; ++i) {
+        sphf[i]   = sph[i];
+        r2[i]     = sph[i].w;
+        sphf[i].w = sph[i].w * 1.0000038146972656f + 1e-30f;     // r*r*(1 + 2^-18) + tiny
+    }
     for (size_t j = 0; j < T; ++j) {
         const Triangle& t = triangles[j];
         // common.rs:128-133,140: n = (v1-v0) x (v2-v0) and d = n.v0 depend on the triangle
@@ -194,6 +207,7 @@ const World::Packed& World::packed() const
         triv[3 * j + 2] = {t.v2.x, t.v2.y, t.v2.z, t.normal.z};
         info[S + j]     = prim_info(t.material, 1.0f);
     }
+    std::memcpy(base + off_plane_b, plane, Tp * sizeof(RtFloat4));
     packed_ = std::move(p);
     return *packed_;
 }

@@ -3,10 +3,16 @@
 // Layout in HBM (one contiguous, 16-byte aligned "scene blob" per device, built once per
 // load_world / World::new and never touched by the render loop again):
 //
-//   [ sph       : float4 x Sp]  {cx, cy, cz, r*r}      hot  — staged into shared memory
-//   [ tri_plane : float4 x Tp]  {n.x, n.y, n.z, n.v0}  hot  — staged into shared memory
-//   [ tri_v     : float4 x 3T]  {v_k.xyz, stored_normal[k]}   warm (plane-stage survivors)
-//   [ info      : 32 B   x P ]  RtPrimInfo             cold (one gather per hit), P = S+T
+//   block A (staged into shared memory by the direct kernels)
+//   [ sph       : float4 x Sp]  {cx, cy, cz, r*r}                 hot
+//   [ tri_plane : float4 x Tp]  {n.x, n.y, n.z, n.v0}             hot
+//   block B (staged instead of A by the exact kernel's FILTER variant, large sphere counts)
+//   [ sph_filter: float4 x Sp]  {cx, cy, cz, r*r*(1+2^-18)+1e-30} hot
+//   [ tri_plane : float4 x Tp]  (same as in block A)              hot
+//   [ sph_r2    : float  x Sp]  r*r                               warm (filter survivors only)
+//   then
+//   [ tri_v     : float4 x 3T]  {v_k.xyz, stored_normal[k]}       warm (plane-stage survivors)
+//   [ info      : 32 B   x P ]  RtPrimInfo                        cold (one gather per hit), P = S+T
 //
 // Sp = S rounded up to a multiple of RT_SPHERE_GROUP, Tp = T rounded up to a multiple of
 // RT_TRI_GROUP; the padding entries are all-NaN, which can never be hit (every comparison
@@ -54,8 +60,10 @@ struct RtPrimInfo {
 
 // Device- or host-resident view of a packed scene (pointers into the blob).
 struct RtSceneView {
-    const RtFloat4*   sph;        // [n_sph_pad]
-    const RtFloat4*   tri_plane;  // [T]
+    const RtFloat4*   sph;        // [n_sph_pad]  block A
+    const RtFloat4*   tri_plane;  // [n_tri_pad]  block A
+    const RtFloat4*   sph_filter; // [n_sph_pad]  block B (followed by tri_plane again, then sph_r2)
+    const float*      sph_r2;     // [n_sph_pad]  block B
     const RtFloat4*   tri_v;      // [3T]
     const RtPrimInfo* info;       // [S+T]
     uint32_t          n_sph;

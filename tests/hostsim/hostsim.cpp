@@ -28,7 +28,7 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
 
     RtFrameParams P{};
     std::memcpy(&P.camera, cam12, sizeof(float) * 12);
-    P.width = W; P.height = H; P.spp = spp; P.depth = depth; P.seed = seed; P.flags = flags;
+    P.width = W; P.height = H; P.spp = spp; P.depth = depth; P.seed = seed; P.flags = flags & 0x7fffffffu;   // bit 31: run the FILTER variant of the exact policy
     P.wm1 = (float)(W - 1u); P.hm1 = (float)(H - 1u);
     P.sample_begin = sample_begin;
     P.resolve_spp  = resolve_spp ? resolve_spp : sample_begin + spp;
@@ -41,7 +41,9 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
             Lane L{};
             begin_pixel(L, P, column, H - 1u - image_row, image_row * W + column);
             // the kernel's loop for one lane: one ray segment per iteration until the pixel is complete
-            while (trace && L.sample < spp) rays += trace_segment<false>(L, P, G, G.sph, G.tri_plane);
+            while (trace && L.sample < spp) rays += (flags & 0x80000000u)
+                                                           ? trace_segment<false, true>(L, P, G, G.sph_filter, G.sph_r2, G.tri_plane)
+                                                           : trace_segment<false, false>(L, P, G, G.sph, nullptr, G.tri_plane);
             out32[L.out_index] = resolve_pixel<false>(L.acc_r, L.acc_g, L.acc_b, pixel_alpha(1.0f, spp > 0 ? spp : 0),
                                                       P.resolve_spp);
         }

@@ -148,7 +148,7 @@ def test_scene_too_large_for_shared_memory_uses_global_path(gpu_rt, ob, scenes):
     cam, world = ob.parse_input(text)
     got, st = _render(rt, h, 48, 27, 1, 6)
     want, rays, _ = ob.ray_trace(world, cam, 48, 27, 1, 6)
-    assert st.resident == 0 and st.rays == rays and np.array_equal(got, want)
+    assert st.resident == 0 and st.filtered == 1 and st.rays == rays and np.array_equal(got, want)
 
 
 def test_shared_reciprocal_divide_equals_ieee_divide(gpu_rt):
@@ -343,13 +343,13 @@ def test_c3_c5_reduced_spp_full_resolution_bands(gpu_rt, ob, scenes):
     """Configs 3 and 5 at reduced size still run the 1,000- / 10,000-primitive scenes
     bit-exactly (shared-memory staged list; triangles through the Mesh path)."""
     rt = gpu_rt
-    for key, W, H, spp, depth in (("c3", 240, 135, 1, 8), ("c5", 64, 36, 1, 16)):
+    for key, W, H, spp, depth in (("c3", 480, 270, 2, 8), ("c5", 96, 54, 2, 16)):
         text = cases.scene_text(scenes, key)
         h = rt.load_world(text)
         cam, world = ob.parse_input(text)
         got, st = _render(rt, h, W, H, spp, depth)
         want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
-        assert st.resident == 1 and st.rays == rays and np.array_equal(got, want), key
+        assert st.resident == 1 and st.filtered == 1 and st.rays == rays and np.array_equal(got, want), key
 
 
 def test_one_process_many_gpus_peer_store_gather(gpu_rt, ob, scenes):

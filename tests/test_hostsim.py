@@ -40,6 +40,21 @@ def test_device_header_on_host_equals_oracle(hostsim, ob, scenes, case):
     assert np.array_equal(out, want)
 
 
+@pytest.mark.parametrize("key,W,H,spp,depth", [("c3", 64, 36, 2, 8), ("c5mini", 48, 27, 2, 16), ("example", 80, 80, 3, 8)])
+def test_filter_variant_of_the_exact_policy_equals_oracle(hostsim, ob, scenes, key, W, H, spp, depth):
+    """The conservative FMA sphere filter (block B, sphere_filter_group) in front of the exact
+    test must not change a single bit or ray count."""
+    cam, world = cases.oracle_scene(ob, scenes, key, "file")
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    out = np.zeros((H, W, 4), np.uint8)
+    n = C.c_uint64()
+    cf = cam.floats()
+    rc = hostsim.hostsim_render(cases.scene_text(scenes, key).encode(), cf.ctypes.data_as(C.POINTER(C.c_float)), W, H,
+                                spp, depth, ob.SEED_DEFAULT, 0x80000000, 0, 0, out.ctypes.data, C.byref(n))
+    assert rc == 0 and n.value == rays
+    assert np.array_equal(out, want)
+
+
 @pytest.mark.parametrize("W,H,spp,depth", [(1, 1, 2, 4), (2, 2, 1, 8), (5, 3, 0, 8), (5, 3, 2, 0), (7, 1, 1, 3), (1, 9, 1, 3)])
 def test_degenerate_frames(hostsim, ob, scenes, W, H, spp, depth):
     """W or H of 1 divides by zero in common.rs:335-336 (NaN rays -> black), spp 0 resolves 0/0,
