@@ -121,7 +121,7 @@ __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_
 #define RT_MIN_CTAS_SMALL 4   // 256-thread CTAs per SM the register allocation must allow (<= 64 registers)
 #endif
 
-template <bool FAST, bool SMEM, int BLOCK, bool FILTER>
+template <bool FAST, bool SMEM, int BLOCK, bool FILTER, bool TRIS>
 __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) rt_render_kernel(const __grid_constant__ RtFrameParams P,
                                                          const __grid_constant__ RtSceneView  G)
 {
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) r
         if (__ballot_sync(FULL, L.have) == 0u) break;
 
         // ---- 2. one ray segment per live lane (sample start, World::hit, scatter, accumulate) ----
-        if (L.have && trace) segments += trace_segment<FAST, FILTER>(L, P, G, sph, sph_r2, tri_plane);
+        if (L.have && trace) segments += trace_segment<FAST, FILTER, TRIS>(L, P, G, sph, sph_r2, tri_plane);
 
         // ---- 3. resolve + pack when the pixel is complete ----
         if (L.have && (!trace || L.sample >= P.spp)) {
@@ -229,36 +229,37 @@ constexpr int      kBlockLarge    = 1024;
 constexpr size_t   kLargeSmemFrom = 56 * 1024;   // above this, < 4 CTAs of 256 threads would fit
 constexpr uint32_t kFilterFrom    = 64;          // spheres from which the exact kernel filters first
 
-struct RenderVariant { bool smem; int block; bool filter; size_t hot_bytes; };
+struct RenderVariant { bool smem; int block; bool filter; bool tris; size_t hot_bytes; };
 
 template <bool FAST>
 inline RenderVariant choose_variant(const RtSceneView& G, size_t smem_limit)
 {
     RenderVariant v;
     v.filter    = !FAST && G.n_sph_pad >= kFilterFrom;
+    v.tris      = G.n_tri_pad > 0;
     v.hot_bytes = rt_hot_bytes(G, v.filter);
     v.smem      = v.hot_bytes <= smem_limit;
     v.block     = (v.smem && v.hot_bytes > kLargeSmemFrom) ? kBlockLarge : kBlockSmall;
     return v;
 }
 
-// f(kernel pointer, block) for the variant's instantiation
+// f(kernel pointer, block) for the variant's instantiation.  FILTER variants exist for the
+// exact policy only; worlds without triangles get kernels without the triangle code.
+template <bool FAST, bool SMEM, int BLOCK, class F>
+cudaError_t with_kernel3(const RenderVariant& v, F&& f)
+{
+    constexpr bool X = !FAST;
+    if (v.filter && X) return v.tris ? f(rt_render_kernel<FAST, SMEM, BLOCK, X, true>, BLOCK)
+                                     : f(rt_render_kernel<FAST, SMEM, BLOCK, X, false>, BLOCK);
+    return v.tris ? f(rt_render_kernel<FAST, SMEM, BLOCK, false, true>, BLOCK)
+                  : f(rt_render_kernel<FAST, SMEM, BLOCK, false, false>, BLOCK);
+}
 template <bool FAST, class F>
 cudaError_t with_kernel(const RenderVariant& v, F&& f)
 {
-    if (FAST) {
-        if (!v.smem) return f(rt_render_kernel<FAST, false, kBlockSmall, false>, kBlockSmall);
-        if (v.block == kBlockLarge) return f(rt_render_kernel<FAST, true, kBlockLarge, false>, kBlockLarge);
-        return f(rt_render_kernel<FAST, true, kBlockSmall, false>, kBlockSmall);
-    }
-    constexpr bool X = !FAST;   // FILTER variants exist for the exact policy only
-    if (!v.smem) return v.filter ? f(rt_render_kernel<FAST, false, kBlockSmall, X>, kBlockSmall)
-                                 : f(rt_render_kernel<FAST, false, kBlockSmall, false>, kBlockSmall);
-    if (v.block == kBlockLarge)
-        return v.filter ? f(rt_render_kernel<FAST, true, kBlockLarge, X>, kBlockLarge)
-                        : f(rt_render_kernel<FAST, true, kBlockLarge, false>, kBlockLarge);
-    return v.filter ? f(rt_render_kernel<FAST, true, kBlockSmall, X>, kBlockSmall)
-                    : f(rt_render_kernel<FAST, true, kBlockSmall, false>, kBlockSmall);
+    if (!v.smem) return with_kernel3<FAST, false, kBlockSmall>(v, f);
+    if (v.block == kBlockLarge) return with_kernel3<FAST, true, kBlockLarge>(v, f);
+    return with_kernel3<FAST, true, kBlockSmall>(v, f);
 }
 
 // Host-side launcher for one policy.

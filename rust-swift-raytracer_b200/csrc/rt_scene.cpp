@@ -131,6 +131,7 @@ RtSceneView World::Packed::view(const unsigned char* base) const
     v.tri_plane = reinterpret_cast<const RtFloat4*>(base + off_tri_plane);
     v.sph_filter = reinterpret_cast<const RtFloat4*>(base + off_sph_filter);
     v.sph_r2     = reinterpret_cast<const float*>(base + off_sph_r2);
+    v.tri_cull  = reinterpret_cast<const RtFloat4*>(base + off_tri_cull);
     v.tri_v     = reinterpret_cast<const RtFloat4*>(base + off_tri_v);
     v.info      = reinterpret_cast<const RtPrimInfo*>(base + off_info);
     v.n_sph     = n_sph;
@@ -153,6 +154,53 @@ RtPrimInfo prim_info(const Material& m, float radius)
 }
 }   // namespace
 
+// Conservative edge-stage reject data of one triangle (rt_trace.cuh, triangle_group).
+// The reference's three inside tests (common.rs:147-163) are  n.(E_k x (p - v_k)) >= 0  with
+// n = (v1-v0)x(v2-v0); divided by |n|^2 these are the barycentric coordinates of p's projection
+// onto the triangle's plane:  lambda2 = f0/|n|^2,  lambda0 = f1/|n|^2,  lambda1 = f2/|n|^2, each
+// an affine function  G.p + g  of p.  The kernel evaluates lambda2 and lambda0 approximately and
+// rejects p when one coordinate is below -0.5 (lambda1 = 1 - lambda0 - lambda2), i.e. when p is
+// outside the triangle by at least half of the corresponding height — provided the operands are
+// small enough for every rounding error (of this approximation AND of the reference's own
+// float evaluation, <= 12u |p - v_k| / h_k) to stay below 0.02: |o|_1 + t + |v0|_1 < 2^12 h_min,
+// which the kernel checks as  |o|_1 + t < K.  Degenerate, needle-thin (K <= 0) or non-finite
+// triangles get K = -inf and are never rejected.  Evaluated in double, rounded once.
+namespace {
+void triangle_cull_record(const Triangle& t, RtFloat4 out[3])
+{
+    const double v0[3] = {t.v0.x, t.v0.y, t.v0.z}, v1[3] = {t.v1.x, t.v1.y, t.v1.z}, v2[3] = {t.v2.x, t.v2.y, t.v2.z};
+    auto subd   = [](const double a[3], const double b[3], double r[3]) { for (int i = 0; i < 3; ++i) r[i] = a[i] - b[i]; };
+    auto crossd = [](const double a[3], const double b[3], double r[3]) {
+        r[0] = a[1] * b[2] - a[2] * b[1]; r[1] = a[2] * b[0] - a[0] * b[2]; r[2] = a[0] * b[1] - a[1] * b[0]; };
+    auto dotd   = [](const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    double e0[3], eb[3], e1[3], n[3], g2[3], g0[3];
+    subd(v1, v0, e0); subd(v2, v0, eb); subd(v2, v1, e1);
+    crossd(e0, eb, n);
+    const double nn = dotd(n, n);
+    const float  ninf = -INFINITY;
+    out[0] = {0.f, 0.f, 0.f, 0.f}; out[1] = {0.f, 0.f, 0.f, 0.f}; out[2] = {ninf, 0.f, 0.f, 0.f};
+    if (!(nn > 0.0) || !std::isfinite(nn)) return;
+    crossd(n, e0, g2);                       // f0 = n.(e0 x (p - v0)) = (n x e0).(p - v0)
+    crossd(n, e1, g0);                       // f1 = n.(e1 x (p - v1)) = (n x e1).(p - v1)
+    for (int i = 0; i < 3; ++i) { g2[i] /= nn; g0[i] /= nn; }
+    const double c2 = -dotd(g2, v0), c0 = -dotd(g0, v1);
+    // heights: h_k = |n| / |edge_k|
+    double e2[3]; subd(v0, v2, e2);
+    const double ln = std::sqrt(nn);
+    const double lmax = std::sqrt(std::max(dotd(e0, e0), std::max(dotd(e1, e1), dotd(e2, e2))));
+    const double hmin = ln / lmax;
+    const double a0 = std::fabs(v0[0]) + std::fabs(v0[1]) + std::fabs(v0[2]);
+    const double a1 = std::fabs(v1[0]) + std::fabs(v1[1]) + std::fabs(v1[2]);
+    const double a2 = std::fabs(v2[0]) + std::fabs(v2[1]) + std::fabs(v2[2]);
+    const double K = 4096.0 * hmin - std::max(a0, std::max(a1, a2));
+    out[0] = {(float)g2[0], (float)g2[1], (float)g2[2], (float)c2};
+    out[1] = {(float)g0[0], (float)g0[1], (float)g0[2], (float)c0};
+    const bool finite = std::isfinite(out[0].x) && std::isfinite(out[0].y) && std::isfinite(out[0].z) && std::isfinite(out[0].w) &&
+                        std::isfinite(out[1].x) && std::isfinite(out[1].y) && std::isfinite(out[1].z) && std::isfinite(out[1].w);
+    if (finite && K > 0.0 && std::isfinite(K)) out[2].x = std::nextafterf((float)K, ninf);
+}
+}   // namespace
+
 // Scene pack: AoS {Sphere, Triangle} -> the SoA blob of rt_types.h.
 const World::Packed& World::packed() const
 {
@@ -171,6 +219,7 @@ const World::Packed& World::packed() const
     p->off_sph_filter = off; off += Sp * sizeof(RtFloat4);
     const size_t off_plane_b = off; off += Tp * sizeof(RtFloat4);
     p->off_sph_r2    = off; off += align_up(Sp * sizeof(float), 16);
+    p->off_tri_cull  = off; off += 3 * T * sizeof(RtFloat4);
     p->off_tri_v     = off; off += 3 * T * sizeof(RtFloat4);
     off = align_up(off, 32);
     p->off_info      = off; off += P * sizeof(RtPrimInfo);
@@ -179,6 +228,7 @@ const World::Packed& World::packed() const
     auto* sph   = reinterpret_cast<RtFloat4*>(base + p->off_sph);
     auto* plane = reinterpret_cast<RtFloat4*>(base + p->off_tri_plane);
     auto* triv  = reinterpret_cast<RtFloat4*>(base + p->off_tri_v);
+    auto* cull  = reinterpret_cast<RtFloat4*>(base + p->off_tri_cull);
     auto* info  = reinterpret_cast<RtPrimInfo*>(base + p->off_info);
     for (size_t i = 0; i < S; ++i) {
         const Sphere& s = spheres[i];
@@ -206,6 +256,7 @@ const World::Packed& World::packed() const
         triv[3 * j + 1] = {t.v1.x, t.v1.y, t.v1.z, t.normal.y};
         triv[3 * j + 2] = {t.v2.x, t.v2.y, t.v2.z, t.normal.z};
         info[S + j]     = prim_info(t.material, 1.0f);
+        triangle_cull_record(t, &cull[3 * j]);
     }
     std::memcpy(base + off_plane_b, plane, Tp * sizeof(RtFloat4));
     packed_ = std::move(p);

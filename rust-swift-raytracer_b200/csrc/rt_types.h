@@ -11,7 +11,9 @@
 //   [ tri_plane : float4 x Tp]  (same as in block A)              hot
 //   [ sph_r2    : float  x Sp]  r*r                               warm (filter survivors only)
 //   then
-//   [ tri_v     : float4 x 3T]  {v_k.xyz, stored_normal[k]}       warm (plane-stage survivors)
+//   [ tri_cull  : float4 x 3T]  {G2.xyz, g2}, {G0.xyz, g0}, {K,0,0,0}: approximate barycentric
+//                               gradients for the conservative edge-stage reject   warm (plane-stage survivors)
+//   [ tri_v     : float4 x 3T]  {v_k.xyz, stored_normal[k]}       cool (reject survivors)
 //   [ info      : 32 B   x P ]  RtPrimInfo                        cold (one gather per hit), P = S+T
 //
 // Sp = S rounded up to a multiple of RT_SPHERE_GROUP, Tp = T rounded up to a multiple of
@@ -64,6 +66,7 @@ struct RtSceneView {
     const RtFloat4*   tri_plane;  // [n_tri_pad]  block A
     const RtFloat4*   sph_filter; // [n_sph_pad]  block B (followed by tri_plane again, then sph_r2)
     const float*      sph_r2;     // [n_sph_pad]  block B
+    const RtFloat4*   tri_cull;   // [3T]
     const RtFloat4*   tri_v;      // [3T]
     const RtPrimInfo* info;       // [S+T]
     uint32_t          n_sph;
