@@ -21,6 +21,9 @@ extern "C" {
 #define RT_OPT_ACCUM_IN     0x4u  /* continue from device_accum (progressive pass) */
 #define RT_OPT_ACCUM_OUT    0x8u  /* store the float4 sums back to device_accum */
 #define RT_OPT_NO_RESOLVE   0x10u /* skip the RGBA8 pack (intermediate progressive pass) */
+#define RT_OPT_PIXEL_ITEMS  0x40u /* scheduling only: a lane always owns a whole pixel */
+#define RT_OPT_SAMPLE_ITEMS 0x80u /* scheduling only: work items are single samples, summed in order by a
+                                     second kernel (default: chosen from the scene and frame size) */
 #define RT_OPT_FULL_FRAME_OUT 0x20u /* rt_render_device with shard_count > 1: device_pixels / device_accum are
                                        FULL width*height frames (e.g. another GPU's frame mapped through CUDA IPC
                                        or peer access); this shard's tiles are stored at their frame offsets */
@@ -44,6 +47,8 @@ typedef struct RtRenderStats {
   uint32_t devices;     /* GPUs that rendered this frame */
   uint32_t peer_gather; /* 1: shards stored their tiles straight into device 0's frame (NVLink peer stores) */
   uint32_t filtered;    /* 1: the exact kernel put its conservative FMA filter in front of the sphere tests */
+  uint32_t sample_items;/* 1: work items were single samples; a second kernel summed them in order */
+  uint32_t reserved;
 } RtRenderStats;
 
 /* common.rs:289-294 `Options`, extended.  Zero-initialise, then set struct_size. */

@@ -27,6 +27,8 @@ cudaError_t occupancy_exact(const RtSceneView& G, size_t smem_limit, int* blocks
                             size_t* hot_bytes, int* resident, int* filtered);
 cudaError_t occupancy_fast(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
                            size_t* hot_bytes, int* resident, int* filtered);
+cudaError_t launch_resolve_samples_exact(const RtFrameParams&, cudaStream_t);
+cudaError_t launch_resolve_samples_fast(const RtFrameParams&, cudaStream_t);
 cudaError_t launch_selftest_division(unsigned long long n_per_thread, uint32_t seed, int grid, int block,
                                      unsigned long long* d_mismatches, cudaStream_t);
 cudaError_t launch_ffma_peak(float* out, int iters, int grid, int block, cudaStream_t);
@@ -59,6 +61,7 @@ struct DeviceContext {
     int          next_slot = 0;
     uint32_t*    d_out    = nullptr;   size_t d_out_cap = 0;     // internal frame buffer (pixels)
     unsigned char* h_stage = nullptr;  size_t h_stage_cap = 0;   // pinned staging for pageable destinations
+    RtFloat4*    d_samples = nullptr;  size_t d_samples_cap = 0; // per-sample colours of the sample-item mode
     struct Geometry { int per_sm = 0, block = 0, resident = 0, filtered = 0; size_t hot_bytes = 0; };
     std::map<std::tuple<uint32_t, uint32_t, int>, Geometry> occupancy;   // (Sp, Tp, fast) -> launch geometry
 };
@@ -168,7 +171,8 @@ struct ShardLaunch {
     size_t       out_pixels = 0;
     int          grid = 0, block = 0;
     size_t       hot_bytes = 0, smem_limit = 0;
-    bool         resident = false, filtered = false;
+    bool         resident = false, filtered = false, sample_items = false;
+    uint32_t     launches = 0;
     CounterSlot* slot = nullptr;
     uint32_t*    d_out = nullptr;
 };
@@ -227,6 +231,37 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     P.ray_counter  = &L.slot->rays;
     P.work_counter = &L.slot->work;
 
+    // Work-item granularity.  A lane normally owns a whole pixel (all its samples, summed in
+    // order in registers).  When the frame offers only a few pixels per lane and every ray
+    // segment is expensive (large primitive lists), the drain at the end of the launch — lanes
+    // idle while the last pixels finish — costs a large part of the run; then the work items
+    // become single SAMPLES, their colours go to a buffer in HBM and a second kernel adds them
+    // in sample order (same bits) and resolves.  Costs spp*32 B of HBM traffic per pixel, which
+    // is why it is reserved for scenes whose segments cost thousands of instructions.
+    {
+        const uint64_t lanes_max  = (uint64_t)ctx.num_sms * 2048u / 2u;          // 32 warps/SM at 64 registers
+        const uint64_t pixels     = (uint64_t)L.n_tiles * opt.tile_rows * W;
+        const uint64_t prims      = (uint64_t)scene.view.n_sph + scene.view.n_tri;
+        const uint64_t buf_bytes  = L.out_pixels * (uint64_t)std::max(opt.samples_per_pixel, 0) * sizeof(RtFloat4);
+        const bool     want = opt.sample_items > 0 ||
+                              (opt.sample_items < 0 && prims >= 512 && opt.samples_per_pixel >= 4 &&
+                               pixels < 16u * lanes_max);
+        L.sample_items = want && opt.samples_per_pixel > 0 && opt.max_ray_bounces > 0 && L.n_tiles > 0 &&
+                         buf_bytes <= ((uint64_t)2 << 30) && slots * (uint64_t)opt.samples_per_pixel < 0xffffff00ull;
+        if (L.sample_items) {
+            if (ctx.d_samples_cap < buf_bytes) {
+                RT_CUDA(cudaStreamSynchronize(stream));
+                if (ctx.d_samples) RT_CUDA(cudaFree(ctx.d_samples));
+                ctx.d_samples = nullptr; ctx.d_samples_cap = 0;
+                RT_CUDA(cudaMalloc(&ctx.d_samples, buf_bytes));
+                ctx.d_samples_cap = buf_bytes;
+            }
+            P.flags |= RT_FLAG_SAMPLE_ITEMS;
+            P.samples       = ctx.d_samples;
+            P.sample_stride = (uint32_t)L.out_pixels;
+        }
+    }
+
     // launch geometry: persistent CTAs, resident-CTA count from the occupancy API
     L.smem_limit = ctx.smem_optin > 1024 ? ctx.smem_optin - 1024 : 0;   // static smem: the mbarrier
     auto& occ    = ctx.occupancy[{scene.view.n_sph_pad, scene.view.n_tri_pad, opt.fast_math ? 1 : 0}];
@@ -241,12 +276,13 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     L.resident  = occ.resident != 0;
     L.filtered  = occ.filtered != 0;
     L.block = occ.block;
-    const uint64_t want_ctas = (slots + (uint64_t)L.block - 1) / (uint64_t)L.block;
+    const uint64_t work_slots = L.sample_items ? slots * (uint64_t)opt.samples_per_pixel : slots;
+    const uint64_t want_ctas = (work_slots + (uint64_t)L.block - 1) / (uint64_t)L.block;
     L.grid = (int)std::min<uint64_t>((uint64_t)occ.per_sm * ctx.num_sms, std::max<uint64_t>(want_ctas, 1));
     // Work-queue granularity: a warp takes `reserve` pixel slots per atomicAdd.  Aim for >= 64
     // slabs per warp so that the last slab of the slowest warp is a small part of the frame.
     const uint64_t warps   = (uint64_t)L.grid * (uint64_t)(L.block / 32);
-    uint64_t       reserve = slots / (warps * 64u) / 32u * 32u;
+    uint64_t       reserve = work_slots / (warps * 64u) / 32u * 32u;
     P.reserve = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(reserve, 32u), 256u);
 
     if (L.n_tiles > 0) {
@@ -254,6 +290,11 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
         if (timed) RT_CUDA(cudaEventRecord(ctx.ev0, stream));
         RT_CUDA(opt.fast_math ? launch_render_fast(P, scene.view, L.grid, L.smem_limit, stream)
                               : launch_render_exact(P, scene.view, L.grid, L.smem_limit, stream));
+        L.launches = 1;
+        if (L.sample_items) {
+            RT_CUDA(opt.fast_math ? launch_resolve_samples_fast(P, stream) : launch_resolve_samples_exact(P, stream));
+            L.launches = 2;
+        }
         if (timed) RT_CUDA(cudaEventRecord(ctx.ev1, stream));
     }
     return L;
@@ -345,7 +386,8 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
             RT_CUDA(cudaStreamSynchronize(stream));
             RT_CUDA(cudaEventElapsedTime(&st.kernel_ms, ctx.ev0, ctx.ev1));
             st.rays     = ctx.h_slot->rays;
-            st.launches = 1;
+            st.launches = L.launches;
+            st.sample_items = L.sample_items ? 1u : 0u;
             st.samples  = (opt.samples_per_pixel > 0 && opt.max_ray_bounces > 0)
                               ? shard_pixels(W, H, opt, n_tiles) * (uint64_t)opt.samples_per_pixel : 0;
         }
@@ -473,7 +515,8 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
             RT_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
             st.kernel_ms = std::max(st.kernel_ms, ms);          // devices run concurrently
             st.rays += c.h_slot->rays;
-            st.launches += 1;
+            st.launches += launches[d].launches;
+            st.sample_items = launches[d].sample_items ? 1u : 0u;
             Options o = base; o.shard_index = (uint32_t)d;
             if (base.samples_per_pixel > 0 && base.max_ray_bounces > 0)
                 st.samples += shard_pixels(W, H, o, launches[d].n_tiles) * (uint64_t)base.samples_per_pixel;

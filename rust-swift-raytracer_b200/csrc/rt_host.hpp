@@ -91,6 +91,8 @@ struct RenderStats {
     uint32_t devices    = 1;     // GPUs that rendered this frame
     uint32_t peer_gather = 0;    // 1: shards stored their tiles straight into device 0's frame (NVLink peer stores)
     uint32_t filtered   = 0;     // 1: exact kernel ran its conservative sphere filter (large sphere lists)
+    uint32_t sample_items = 0;   // 1: work items were single samples (ordered sum by the resolve kernel)
+    uint32_t reserved   = 0;
 };
 
 // common.rs:289-294, extended.  The reference fields keep their names.
@@ -114,6 +116,7 @@ struct Options {
     bool     full_frame_out = false;        // sharded, but device_pixels/device_accum are FULL frames (e.g. a
                                             // peer-mapped frame on another GPU): tiles land at their frame offset
     int32_t  n_devices      = 0;            // > 1: one process drives devices 0..n-1 (ray_trace_multi)
+    int32_t  sample_items   = -1;           // work-item granularity: -1 auto, 0 whole pixels, 1 single samples
     RenderStats* stats      = nullptr;
 };
 

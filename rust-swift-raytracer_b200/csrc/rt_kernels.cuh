@@ -92,13 +92,22 @@ struct PixelSlot {
 };
 
 __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_t slot, uint32_t subtiles_x,
-                                                 uint32_t chunks_per_strip)
+                                                 uint32_t chunks_per_strip, uint32_t& sample_of_item)
 {
     // Slots run from the BOTTOM of the frame upwards: rows near the ground carry the long
     // paths, rows of sky end after one segment, so the expensive pixels are handed out first
     // and the tail of the launch (when the queue is empty and lanes drain) is made of cheap
     // ones.  Pure scheduling: every pixel is computed the same way wherever it is in the order.
-    const uint32_t chunk = slot >> 5, in = slot & 31u;
+    // RT_FLAG_SAMPLE_ITEMS: a slot is one SAMPLE of a pixel; 32 consecutive slots are the same
+    // sample of the 32 pixels of an 8x4 sub-tile, the next 32 the following sample of that tile.
+    uint32_t chunk = slot >> 5;
+    const uint32_t in = slot & 31u;
+    sample_of_item = 0u;
+    if (P.flags & RT_FLAG_SAMPLE_ITEMS) {
+        const uint32_t c = chunk / (uint32_t)P.spp;
+        sample_of_item   = chunk - c * (uint32_t)P.spp;
+        chunk            = c;
+    }
     const uint32_t rs    = chunk / chunks_per_strip;
     const uint32_t strip = P.n_tiles - 1u - rs;
     const uint32_t rc    = chunk - rs * chunks_per_strip;
@@ -151,8 +160,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) r
 
     const uint32_t subtiles_x       = (P.width + 7u) >> 3;
     const uint32_t chunks_per_strip = subtiles_x * (P.tile_rows >> 2);
-    const uint32_t total_slots      = P.n_tiles * chunks_per_strip * 32u;
     const bool     trace            = (P.spp > 0) && (P.depth > 0);
+    const bool     items            = (P.flags & RT_FLAG_SAMPLE_ITEMS) != 0;      // host sets it only when trace
+    const uint32_t total_slots      = P.n_tiles * chunks_per_strip * 32u * (items ? (uint32_t)P.spp : 1u);
 
     // warp-uniform slab of reserved pixel slots
     uint32_t pool_next = 0, pool_end = 0;
@@ -182,10 +192,14 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) r
             const uint32_t avail = pool_end - pool_next;
             const uint32_t rank  = __popc(need & lt);
             if (!L.have && rank < avail) {
-                PixelSlot s = decode_slot(P, pool_next + rank, subtiles_x, chunks_per_strip);
+                uint32_t  item_sample;
+                PixelSlot s = decode_slot(P, pool_next + rank, subtiles_x, chunks_per_strip, item_sample);
                 if (s.valid) {
                     begin_pixel(L, P, s.column, P.height - 1u - s.image_row, s.out_index);   // common.rs:351 (flip)
-                    if (P.flags & RT_FLAG_ACCUM_IN) {
+                    if (items) {                       // one sample: sums start at 0, colour goes to the sample buffer
+                        L.sample    = (int32_t)item_sample;
+                        L.out_index = item_sample * P.sample_stride + s.out_index;
+                    } else if (P.flags & RT_FLAG_ACCUM_IN) {
                         RtFloat4 a = ld4(&P.accum[s.out_index]);
                         L.acc_r = a.x; L.acc_g = a.y; L.acc_b = a.z;      // a.w is re-read at the end
                     }
@@ -197,9 +211,22 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) r
         if (__ballot_sync(FULL, L.have) == 0u) break;
 
         // ---- 2. one ray segment per live lane (sample start, World::hit, scatter, accumulate) ----
-        if (L.have && trace) segments += trace_segment<FAST, FILTER, TRIS>(L, P, G, sph, sph_r2, tri_plane);
+        bool sample_done = false;
+        if (L.have && trace) {
+            sample_done = trace_segment<FAST, FILTER, TRIS>(L, P, G, sph, sph_r2, tri_plane);
+            ++segments;
+        }
 
-        // ---- 3. resolve + pack when the pixel is complete ----
+        // ---- 3a. sample items: hand the colour to the ordered-sum kernel ----
+        if (items) {
+            if (L.have && sample_done) {
+                *reinterpret_cast<float4*>(&P.samples[L.out_index]) = make_float4(L.acc_r, L.acc_g, L.acc_b, 1.0f);
+                L.have = false;
+            }
+            continue;
+        }
+
+        // ---- 3b. resolve + pack when the pixel is complete ----
         if (L.have && (!trace || L.sample >= P.spp)) {
             // alpha: 1.0 (or the accumulator's) + one per sample; depth <= 0 still adds spp black samples
             const float a0    = (P.flags & RT_FLAG_ACCUM_IN) ? P.accum[L.out_index].w : 1.0f;
@@ -219,6 +246,46 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) r
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
     if (lane == 0 && P.ray_counter && segs) atomicAdd(P.ray_counter, segs);
+}
+
+// Second kernel of the RT_FLAG_SAMPLE_ITEMS mode: one thread per pixel adds the pixel's sample
+// colours IN SAMPLE ORDER (common.rs:338-340; float addition is not associative, and
+// 0.0f + colour == colour, so the sums are the bits the one-lane-per-pixel kernel produces),
+// then resolves and packs exactly like the render kernel (common.rs:344-356).  HBM-bound:
+// spp*16 B read + 4 B written per pixel, coalesced (a warp reads 512 contiguous bytes per sample).
+template <bool FAST>
+__global__ void __launch_bounds__(256) rt_resolve_samples_kernel(const __grid_constant__ RtFrameParams P)
+{
+    const uint32_t rows_out = P.n_tiles * P.tile_rows;
+    const uint32_t local    = blockIdx.x * blockDim.x + threadIdx.x;          // index among this shard's pixel rows
+    if (local >= rows_out * P.width) return;
+    const uint32_t r = local / P.width, x = local - r * P.width;
+    const uint32_t strip = r / P.tile_rows, yin = r - strip * P.tile_rows;
+    const uint32_t image_row = (P.tile_first + strip * P.tile_stride) * P.tile_rows + yin;
+    if (image_row >= P.height) return;
+    const uint32_t out_row = (P.flags & RT_FLAG_COMPACT_OUT) ? r : image_row;
+    const uint32_t idx     = out_row * P.width + x;
+    float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, a0 = 1.0f;                 // Color::new(0,0,0), common.rs:333
+    if (P.flags & RT_FLAG_ACCUM_IN) {
+        RtFloat4 a = ld4(&P.accum[idx]);
+        acc_r = a.x; acc_g = a.y; acc_b = a.z; a0 = a.w;
+    }
+    for (int32_t s = 0; s < P.spp; ++s) {
+        const float4 c = *reinterpret_cast<const float4*>(&P.samples[(size_t)s * P.sample_stride + idx]);
+        acc_r += c.x; acc_g += c.y; acc_b += c.z;
+    }
+    const float acc_a = pixel_alpha(a0, P.spp);
+    if (P.flags & RT_FLAG_ACCUM_OUT) *reinterpret_cast<float4*>(&P.accum[idx]) = make_float4(acc_r, acc_g, acc_b, acc_a);
+    if (!(P.flags & RT_FLAG_NO_RESOLVE)) P.out[idx] = resolve_pixel<FAST>(acc_r, acc_g, acc_b, acc_a, P.resolve_spp);
+}
+
+template <bool FAST>
+cudaError_t launch_resolve_samples(const RtFrameParams& P, cudaStream_t stream)
+{
+    const uint64_t n = (uint64_t)P.n_tiles * P.tile_rows * P.width;
+    if (n == 0) return cudaSuccess;
+    rt_resolve_samples_kernel<FAST><<<(unsigned)((n + 255u) / 256u), 256, 0, stream>>>(P);
+    return cudaGetLastError();
 }
 
 // Launch geometry.  Small primitive lists leave room for several 256-thread CTAs per SM;

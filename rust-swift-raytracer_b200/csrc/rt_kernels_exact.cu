@@ -13,6 +13,11 @@ cudaError_t launch_render_exact(const RtFrameParams& P, const RtSceneView& G, in
     return launch_render<false>(P, G, grid, smem_limit, stream);
 }
 
+cudaError_t launch_resolve_samples_exact(const RtFrameParams& P, cudaStream_t stream)
+{
+    return launch_resolve_samples<false>(P, stream);
+}
+
 cudaError_t occupancy_exact(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
                             size_t* hot_bytes, int* resident, int* filtered)
 {

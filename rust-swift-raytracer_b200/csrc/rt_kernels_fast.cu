@@ -12,6 +12,11 @@ cudaError_t launch_render_fast(const RtFrameParams& P, const RtSceneView& G, int
     return launch_render<true>(P, G, grid, smem_limit, stream);
 }
 
+cudaError_t launch_resolve_samples_fast(const RtFrameParams& P, cudaStream_t stream)
+{
+    return launch_resolve_samples<true>(P, stream);
+}
+
 cudaError_t occupancy_fast(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
                             size_t* hot_bytes, int* resident, int* filtered)
 {

@@ -82,6 +82,8 @@ enum : uint32_t {
     RT_FLAG_ACCUM_OUT    = 1u << 2,   // write the float4 accumulator back
     RT_FLAG_NO_RESOLVE   = 1u << 3,   // skip the RGBA8 pack (intermediate progressive pass)
     RT_FLAG_COMPACT_OUT  = 1u << 4,   // out/accum hold only this shard's tiles, packed
+    RT_FLAG_SAMPLE_ITEMS = 1u << 5,   // work items are (pixel, sample) pairs; colours go to `samples`, the
+                                      // ordered sum + resolve is done by rt_resolve_samples_kernel
 };
 
 // Everything one render launch needs (passed by value as a __grid_constant__).
@@ -104,4 +106,8 @@ struct RtFrameParams {
     RtFloat4* accum;         // optional float4 sums, same indexing as out
     unsigned long long* ray_counter;   // += number of World::hit calls
     unsigned int* work_counter;        // zeroed before launch
+    // RT_FLAG_SAMPLE_ITEMS: colour of sample s of the pixel with output index i at samples[s*sample_stride + i]
+    RtFloat4* samples;
+    uint32_t  sample_stride;
+    uint32_t  pad1;
 };

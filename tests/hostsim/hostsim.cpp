@@ -41,10 +41,10 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
             Lane L{};
             begin_pixel(L, P, column, H - 1u - image_row, image_row * W + column);
             // the kernel's loop for one lane: one ray segment per iteration until the pixel is complete
-            while (trace && L.sample < spp) rays += (flags & 0x80000000u)
+            while (trace && L.sample < spp) rays += 1, (void)((flags & 0x80000000u)
                                                            ? trace_segment<false, true, true>(L, P, G, G.sph_filter, G.sph_r2, G.tri_plane)
                                                            : (G.n_tri_pad ? trace_segment<false, false, true>(L, P, G, G.sph, nullptr, G.tri_plane)
-                                                                          : trace_segment<false, false, false>(L, P, G, G.sph, nullptr, G.tri_plane));
+                                                                          : trace_segment<false, false, false>(L, P, G, G.sph, nullptr, G.tri_plane)));
             out32[L.out_index] = resolve_pixel<false>(L.acc_r, L.acc_g, L.acc_b, pixel_alpha(1.0f, spp > 0 ? spp : 0),
                                                       P.resolve_spp);
         }

@@ -52,6 +52,54 @@ def test_exact_kernel_equals_oracle_and_golden(gpu_rt, ob, scenes, case):
     assert np.array_equal(got, GOLDEN[name]) and rays == int(GOLDEN[name + "__rays"][0])
 
 
+@pytest.mark.parametrize("case", cases.SMALL_CASES, ids=[c[0] for c in cases.SMALL_CASES])
+def test_sample_item_scheduling_is_bit_identical(gpu_rt, ob, scenes, case):
+    """RT_OPT_SAMPLE_ITEMS: lanes trace single samples, a second kernel adds them in sample order.
+    Pure scheduling — pixels and ray counts must not change by a bit; nor with whole-pixel items
+    forced (RT_OPT_PIXEL_ITEMS)."""
+    rt = gpu_rt
+    name, key, camera, W, H, spp, depth, fixed = case
+    h = cases.product_scene(rt, scenes, key, camera)
+    got, st = _render(rt, h, W, H, spp, depth, fixed_jitter=fixed, sample_items=True)
+    assert st.sample_items == 1 and st.launches == 2
+    assert np.array_equal(got, GOLDEN[name]) and st.rays == int(GOLDEN[name + "__rays"][0])
+    got, st = _render(rt, h, W, H, spp, depth, fixed_jitter=fixed, sample_items=False)
+    assert st.sample_items == 0 and st.launches == 1
+    assert np.array_equal(got, GOLDEN[name]) and st.rays == int(GOLDEN[name + "__rays"][0])
+
+
+def test_sample_items_with_shards_and_progressive_passes(gpu_rt, ob, scenes):
+    import torch
+    rt = gpu_rt
+    W, H = 150, 70
+    h = rt.load_world(scenes.example_world())
+    cam, world = ob.parse_input(scenes.example_world())
+    want, rays, want_acc = ob.ray_trace(world, cam, W, H, 12, 8, want_accum=True)
+    # shards into the caller's frame
+    fb = rt.Framebuffer(W, H)
+    for i in range(3):
+        rt.render_with_options(fb, h, rt.Options(12, 8, shard_index=i, shard_count=3, tile_rows=8, sample_items=True))
+    assert np.array_equal(fb.pixels, want)
+    # 3 progressive passes of 4 spp through the float4 accumulator
+    accum = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    out = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+    for p in range(3):
+        o = rt.Options(4, 8, sample_begin=4 * p, accum_in=p > 0, accum_out=True, no_resolve=p < 2, resolve_spp=12,
+                       sample_items=True)
+        rt.render_device(h, o, W, H, out.data_ptr(), accum.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint8).reshape(H, W, 4), want)
+    assert np.array_equal(accum.cpu().numpy(), want_acc)
+
+
+def test_sample_items_are_chosen_for_heavy_scenes_only(gpu_rt, scenes):
+    rt = gpu_rt
+    _, st = _render(rt, rt.load_world(scenes.c5_world()), 64, 36, 4, 4)
+    assert st.sample_items == 1                          # 10,000 primitives, few pixels per lane
+    _, st = _render(rt, rt.load_world(scenes.default_world()), 64, 36, 4, 4)
+    assert st.sample_items == 0                          # 8 spheres: the HBM round trip would not pay
+
+
 def test_render_abi_call_is_16spp_depth8(gpu_rt, ob, scenes):
     """lib.rs:49-57: render(fb, handle) == Options::new(16, 8); the frame lands in the caller's
     buffer and the returned struct points at it."""
