@@ -42,7 +42,8 @@ namespace {
 }
 #define RT_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) fail(#expr, e_); } while (0)
 
-constexpr int kCounterSlots = 64;
+constexpr int      kCounterSlots    = 64;
+constexpr uint64_t kSampleBufferCap = (uint64_t)1 << 30;
 
 struct CounterSlot {            // 16 B, zeroed by one memset per launch
     unsigned long long rays;
@@ -62,6 +63,7 @@ struct DeviceContext {
     uint32_t*    d_out    = nullptr;   size_t d_out_cap = 0;     // internal frame buffer (pixels)
     unsigned char* h_stage = nullptr;  size_t h_stage_cap = 0;   // pinned staging for pageable destinations
     RtFloat4*    d_samples = nullptr;  size_t d_samples_cap = 0; // per-sample colours of the sample-item mode
+    RtFloat4*    d_accum = nullptr;    size_t d_accum_cap = 0;   // hand-over sums between sample-item chunks
     struct Geometry { int per_sm = 0, block = 0, resident = 0, filtered = 0; size_t hot_bytes = 0; };
     std::map<std::tuple<uint32_t, uint32_t, int>, Geometry> occupancy;   // (Sp, Tp, fast) -> launch geometry
 };
@@ -238,23 +240,40 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     // become single SAMPLES, their colours go to a buffer in HBM and a second kernel adds them
     // in sample order (same bits) and resolves.  Costs spp*32 B of HBM traffic per pixel, which
     // is why it is reserved for scenes whose segments cost thousands of instructions.
+    int32_t chunk_spp = opt.samples_per_pixel;       // samples per launch in sample-item mode
     {
         const uint64_t lanes_max  = (uint64_t)ctx.num_sms * 2048u / 2u;          // 32 warps/SM at 64 registers
         const uint64_t pixels     = (uint64_t)L.n_tiles * opt.tile_rows * W;
         const uint64_t prims      = (uint64_t)scene.view.n_sph + scene.view.n_tri;
-        const uint64_t buf_bytes  = L.out_pixels * (uint64_t)std::max(opt.samples_per_pixel, 0) * sizeof(RtFloat4);
         const bool     want = opt.sample_items > 0 ||
                               (opt.sample_items < 0 && prims >= 512 && opt.samples_per_pixel >= 4 &&
                                pixels < 16u * lanes_max);
-        L.sample_items = want && opt.samples_per_pixel > 0 && opt.max_ray_bounces > 0 && L.n_tiles > 0 &&
-                         buf_bytes <= ((uint64_t)2 << 30) && slots * (uint64_t)opt.samples_per_pixel < 0xffffff00ull;
+        L.sample_items = want && opt.samples_per_pixel > 0 && opt.max_ray_bounces > 0 && L.n_tiles > 0;
         if (L.sample_items) {
+            // the sample buffer is capped (1 GiB): more samples than fit are traced in several
+            // launches that hand their sums on through the float4 accumulator
+            const uint64_t per_sample = L.out_pixels * sizeof(RtFloat4);
+            const uint64_t cap_spp    = std::max<uint64_t>(kSampleBufferCap / std::max<uint64_t>(per_sample, 1), 1);
+            const uint64_t slot_spp   = std::max<uint64_t>(0xffffff00ull / std::max<uint64_t>(slots, 1), 1) - 0;
+            chunk_spp = (int32_t)std::min<uint64_t>({(uint64_t)opt.samples_per_pixel, cap_spp, slot_spp});
+            const uint64_t buf_bytes = per_sample * (uint64_t)chunk_spp;
             if (ctx.d_samples_cap < buf_bytes) {
                 RT_CUDA(cudaStreamSynchronize(stream));
                 if (ctx.d_samples) RT_CUDA(cudaFree(ctx.d_samples));
                 ctx.d_samples = nullptr; ctx.d_samples_cap = 0;
                 RT_CUDA(cudaMalloc(&ctx.d_samples, buf_bytes));
                 ctx.d_samples_cap = buf_bytes;
+            }
+            if (chunk_spp < opt.samples_per_pixel && !P.accum) {      // internal hand-over accumulator
+                const size_t need = L.out_pixels * sizeof(RtFloat4);
+                if (ctx.d_accum_cap < need) {
+                    RT_CUDA(cudaStreamSynchronize(stream));
+                    if (ctx.d_accum) RT_CUDA(cudaFree(ctx.d_accum));
+                    ctx.d_accum = nullptr; ctx.d_accum_cap = 0;
+                    RT_CUDA(cudaMalloc(&ctx.d_accum, need));
+                    ctx.d_accum_cap = need;
+                }
+                P.accum = ctx.d_accum;
             }
             P.flags |= RT_FLAG_SAMPLE_ITEMS;
             P.samples       = ctx.d_samples;
@@ -276,7 +295,7 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     L.resident  = occ.resident != 0;
     L.filtered  = occ.filtered != 0;
     L.block = occ.block;
-    const uint64_t work_slots = L.sample_items ? slots * (uint64_t)opt.samples_per_pixel : slots;
+    const uint64_t work_slots = L.sample_items ? slots * (uint64_t)chunk_spp : slots;
     const uint64_t want_ctas = (work_slots + (uint64_t)L.block - 1) / (uint64_t)L.block;
     L.grid = (int)std::min<uint64_t>((uint64_t)occ.per_sm * ctx.num_sms, std::max<uint64_t>(want_ctas, 1));
     // Work-queue granularity: a warp takes `reserve` pixel slots per atomicAdd.  Aim for >= 64
@@ -288,12 +307,28 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     if (L.n_tiles > 0) {
         RT_CUDA(cudaMemsetAsync(L.slot, 0, sizeof(CounterSlot), stream));
         if (timed) RT_CUDA(cudaEventRecord(ctx.ev0, stream));
-        RT_CUDA(opt.fast_math ? launch_render_fast(P, scene.view, L.grid, L.smem_limit, stream)
-                              : launch_render_exact(P, scene.view, L.grid, L.smem_limit, stream));
-        L.launches = 1;
-        if (L.sample_items) {
-            RT_CUDA(opt.fast_math ? launch_resolve_samples_fast(P, stream) : launch_resolve_samples_exact(P, stream));
-            L.launches = 2;
+        if (!L.sample_items) {
+            RT_CUDA(opt.fast_math ? launch_render_fast(P, scene.view, L.grid, L.smem_limit, stream)
+                                  : launch_render_exact(P, scene.view, L.grid, L.smem_limit, stream));
+            L.launches = 1;
+        } else {
+            // sample items: [trace chunk_spp samples -> ordered sum] per chunk, sums handed on in P.accum
+            const uint32_t user_flags = P.flags;
+            const int32_t  total = opt.samples_per_pixel;
+            for (int32_t done = 0; done < total; done += chunk_spp) {
+                const bool first = done == 0, last = done + chunk_spp >= total;
+                P.spp          = std::min(chunk_spp, total - done);
+                P.sample_begin = opt.sample_begin + done;
+                P.flags        = user_flags & ~(RT_FLAG_ACCUM_IN | RT_FLAG_ACCUM_OUT | RT_FLAG_NO_RESOLVE);
+                if (!first || (user_flags & RT_FLAG_ACCUM_IN)) P.flags |= RT_FLAG_ACCUM_IN;
+                if (!last || (user_flags & RT_FLAG_ACCUM_OUT)) P.flags |= RT_FLAG_ACCUM_OUT;
+                if (!last || (user_flags & RT_FLAG_NO_RESOLVE)) P.flags |= RT_FLAG_NO_RESOLVE;
+                if (!first) RT_CUDA(cudaMemsetAsync(&L.slot->work, 0, sizeof(unsigned int), stream));
+                RT_CUDA(opt.fast_math ? launch_render_fast(P, scene.view, L.grid, L.smem_limit, stream)
+                                      : launch_render_exact(P, scene.view, L.grid, L.smem_limit, stream));
+                RT_CUDA(opt.fast_math ? launch_resolve_samples_fast(P, stream) : launch_resolve_samples_exact(P, stream));
+                L.launches += 2;
+            }
         }
         if (timed) RT_CUDA(cudaEventRecord(ctx.ev1, stream));
     }

@@ -367,6 +367,9 @@ def test_c2_full_size_properties(gpu_rt, ob, scenes):
         rt.render_device(h, o, W, H, out.data_ptr(), accum.data_ptr(), 0)
     torch.cuda.synchronize()
     assert _sha(out.cpu().numpy()) == _sha(a)
+    # sample-item scheduling at a size where the 1 GiB sample buffer forces two chunks (2 x 32 spp)
+    c, st3 = _render(rt, h, W, H, spp, depth, pinned=True, sample_items=True)
+    assert st3.sample_items == 1 and st3.launches == 4 and st3.rays == st.rays and _sha(c) == _sha(a)
     # oracle at full resolution, 1 spp (the per-sample RNG makes every sample independent)
     cam, world = ob.parse_input(scenes.default_world())
     small, _, _ = ob.ray_trace(world, cam, W, H, 1, depth)
