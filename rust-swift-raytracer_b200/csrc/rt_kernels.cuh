@@ -294,7 +294,7 @@ cudaError_t launch_resolve_samples(const RtFrameParams& P, cudaStream_t stream)
 constexpr int      kBlockSmall    = 256;
 constexpr int      kBlockLarge    = 1024;
 constexpr size_t   kLargeSmemFrom = 56 * 1024;   // above this, < 4 CTAs of 256 threads would fit
-constexpr uint32_t kFilterFrom    = 64;          // spheres from which the exact kernel filters first
+constexpr uint32_t kFilterFrom    = 64;          // spheres from which the kernels filter first
 
 struct RenderVariant { bool smem; int block; bool filter; bool tris; size_t hot_bytes; };
 
@@ -302,7 +302,7 @@ template <bool FAST>
 inline RenderVariant choose_variant(const RtSceneView& G, size_t smem_limit)
 {
     RenderVariant v;
-    v.filter    = !FAST && G.n_sph_pad >= kFilterFrom;
+    v.filter    = G.n_sph_pad >= kFilterFrom;
     v.tris      = G.n_tri_pad > 0;
     v.hot_bytes = rt_hot_bytes(G, v.filter);
     v.smem      = v.hot_bytes <= smem_limit;
@@ -310,14 +310,13 @@ inline RenderVariant choose_variant(const RtSceneView& G, size_t smem_limit)
     return v;
 }
 
-// f(kernel pointer, block) for the variant's instantiation.  FILTER variants exist for the
-// exact policy only; worlds without triangles get kernels without the triangle code.
+// f(kernel pointer, block) for the variant's instantiation.  Large sphere lists get the
+// FILTER kernels; worlds without triangles get kernels without the triangle code.
 template <bool FAST, bool SMEM, int BLOCK, class F>
 cudaError_t with_kernel3(const RenderVariant& v, F&& f)
 {
-    constexpr bool X = !FAST;
-    if (v.filter && X) return v.tris ? f(rt_render_kernel<FAST, SMEM, BLOCK, X, true>, BLOCK)
-                                     : f(rt_render_kernel<FAST, SMEM, BLOCK, X, false>, BLOCK);
+    if (v.filter) return v.tris ? f(rt_render_kernel<FAST, SMEM, BLOCK, true, true>, BLOCK)
+                                : f(rt_render_kernel<FAST, SMEM, BLOCK, true, false>, BLOCK);
     return v.tris ? f(rt_render_kernel<FAST, SMEM, BLOCK, false, true>, BLOCK)
                   : f(rt_render_kernel<FAST, SMEM, BLOCK, false, false>, BLOCK);
 }

@@ -242,9 +242,15 @@ const World::Packed& World::packed() const
     auto* sphf = reinterpret_cast<RtFloat4*>(base + p->off_sph_filter);
     auto* r2   = reinterpret_cast<float*>(base + p->off_sph_r2);
     for (size_t i = 0; i < Sp; ++i) {
-        sphf[i]   = sph[i];
-        r2[i]     = sph[i].w;
-        sphf[i].w = sph[i].w * 1.0000038146972656f + 1e-30f;     // r*r*(1 + 2^-18) + tiny
+        sphf[i] = sph[i];
+        r2[i]   = sph[i].w;
+        // w = c.c - r^2 - 2^-17 (c.c + r^2), in double, rounded DOWN (a smaller w only lets more spheres through)
+        const double cc = (double)sph[i].x * sph[i].x + (double)sph[i].y * sph[i].y + (double)sph[i].z * sph[i].z;
+        const double rr = (double)sph[i].w;
+        const double w  = cc - rr - (cc + rr) * (1.0 / 131072.0) - 1e-30;
+        float wf = (float)w;
+        if ((double)wf > w) wf = std::nextafterf(wf, -INFINITY);
+        sphf[i].w = wf;                                            // NaN padding stays NaN
     }
     for (size_t j = 0; j < T; ++j) {
         const Triangle& t = triangles[j];

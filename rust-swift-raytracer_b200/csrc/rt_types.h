@@ -6,8 +6,8 @@
 //   block A (staged into shared memory by the direct kernels)
 //   [ sph       : float4 x Sp]  {cx, cy, cz, r*r}                 hot
 //   [ tri_plane : float4 x Tp]  {n.x, n.y, n.z, n.v0}             hot
-//   block B (staged instead of A by the exact kernel's FILTER variant, large sphere counts)
-//   [ sph_filter: float4 x Sp]  {cx, cy, cz, r*r*(1+2^-18)+1e-30} hot
+//   block B (staged instead of A by the FILTER kernels, large sphere counts)
+//   [ sph_filter: float4 x Sp]  {cx, cy, cz, c.c - r*r - margin}  hot  (rt_trace.cuh, sphere_filter_group)
 //   [ tri_plane : float4 x Tp]  (same as in block A)              hot
 //   [ sph_r2    : float  x Sp]  r*r                               warm (filter survivors only)
 //   then
