@@ -50,6 +50,11 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one render-kernel launch, from the committed
+# `ncu --set full` captures (profiles/r01_bench.md); None where no capture of that exact launch exists.
+NCU_TRAFFIC_BYTES = {("c2", False): 36352}      # 36 KB read, 0 B written: the 8.3 MB frame stays in the 126 MB L2
+
+
 def scene_text(scenes, key):
     return {"default": scenes.default_world, "c3": scenes.c3_world, "c5": scenes.c5_world}[key]()
 
@@ -207,6 +212,9 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = render kernels store their tiles into rank 0's frame over NVLink "
                          "(CUDA IPC mapping); 'nccl' = compact buffers + one dist.gather")
+    ap.add_argument("--devices", type=int, default=0,
+                    help="N = 1 launch only: e2e through render_with_options(n_devices=D), ONE process driving D GPUs "
+                         "(the shape the C-ABI callers have); reported under e2e_one_process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -327,6 +335,22 @@ def main():
                "api": "render_with_options (C ABI, pinned host framebuffer)" if (n_gpus == 1 and passes == 1)
                       else f"multi.ShardedRenderer.render(to_host=True): tile shards -> {renderer.gather} gather -> D2H on rank 0"}
 
+    one_process = None
+    if args.devices > 1 and n_gpus == 1 and passes == 1:
+        fbm = rt.Framebuffer(W, H, pinned=True)
+        om = rt.Options(spp, depth, fast_math=fast, n_devices=args.devices)
+        stm = rt.RenderStats()
+        rt.render_with_options(fbm, handle, om, stm)
+        tot = 0.0
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            rt.render_with_options(fbm, handle, om)
+            tot += time.perf_counter() - t0
+        one_process = {"devices": int(stm.devices), "peer_gather": int(stm.peer_gather),
+                       "value": rays_frame / (tot / args.steps) / 1e6, "unit": "Mrays/s",
+                       "ms_per_frame": tot / args.steps * 1e3, "d2h_bytes_per_step": W * H * 4,
+                       "api": "render_with_options(n_devices=D): one process, tiles stored into device 0's frame "
+                              "over NVLink peer mappings, one D2H"}
     renderer.close()
     if rank != 0:
         if n_gpus > 1:
@@ -351,7 +375,8 @@ def main():
         "e2e": e2e,
         "gpu_launches": args.steps * passes,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak * n_gpus, "unit": "TFLOP/s",
-                     "frac": achieved / (fp32_peak * n_gpus) if fp32_peak else None, "traffic": None,
+                     "frac": achieved / (fp32_peak * n_gpus) if fp32_peak else None,
+                     "traffic": NCU_TRAFFIC_BYTES.get((args.workload, fast)) if (n_gpus == 1 and not args.spp) else None,
                      "peak_source": "FFMA-chain microbenchmark run on this GPU before the timed region "
                                     "(MEASURED_PEAKS.json has no FP32 CUDA-core figure; nominal 2*128*148*1.965 GHz = 74.4)",
                      "flops_per_step": flops,
@@ -359,6 +384,8 @@ def main():
                      "hbm_bytes_per_step": W * H * 4 + (passes - 1) * 2 * W * H * 16},
         "clocks": clocks.summary(),
     }
+    if one_process:
+        line["e2e_one_process"] = one_process
     if not args.no_cpu_baseline and n_gpus == 1:
         line["cpu_baseline"] = cpu_baseline_serial(scenes, wl)
     print(json.dumps(line), flush=True)
