@@ -89,7 +89,10 @@ struct Rust_Camera *move_camera_position(struct Rust_Camera *camera, float x, fl
  * provides: GameView.swift:125-129,350-354, c_raytracer.rs:53-58) and the same struct is
  * returned — a defined superset of the reference, whose returned `pixels` dangles
  * (lib.rs:79-87).  Reads handle->camera at call time.  On failure (no CUDA device, CUDA
- * error) the pixels are left untouched and rt_last_error() is set. */
+ * error) the pixels are left untouched and rt_last_error() is set.
+ * Environment, for callers that cannot pass options: RT_GPUS=N renders the frame on N GPUs
+ * (row tiles, stored straight into device 0's frame over NVLink); RT_DETERMINISTIC=1 uses the
+ * fixed sub-pixel offset (0.5, 0.5) instead of the two jitter draws. */
 struct Rust_CFramebuffer render(struct Rust_CFramebuffer framebuffer,
                                 const struct Rust_WorldHandle *handle);
 

@@ -32,7 +32,13 @@ int env_devices()
 rt::Options to_options(const RtRenderOptions* o)
 {
     rt::Options r;
-    if (!o) { r.samples_per_pixel = 16; r.max_ray_bounces = 8; return r; }   // lib.rs:51
+    if (!o) {                                        // render(): Options::new(16, 8, None, true), lib.rs:51
+        r.samples_per_pixel = 16; r.max_ray_bounces = 8;
+        // an unchanged caller of render() can still ask for the deterministic mode (fixed sub-pixel offset)
+        const char* det = std::getenv("RT_DETERMINISTIC");
+        r.fixed_jitter = det && *det && *det != '0';
+        return r;
+    }
     RtRenderOptions c;
     std::memset(&c, 0, sizeof c);
     std::memcpy(&c, o, o->struct_size && o->struct_size < sizeof c ? o->struct_size : sizeof c);
