@@ -127,6 +127,20 @@ size_t rt_world_triangle_count(const struct Rust_WorldHandle *handle);
 int rt_world_get_sphere(const struct Rust_WorldHandle *handle, size_t index, float out9[9]);
 int rt_world_get_triangle(const struct Rust_WorldHandle *handle, size_t index, float out18[18]);
 
+/* load_world with opt-in grammar extensions (load_world itself accepts exactly the reference's
+ * grammar and rejects everything the reference rejects).  RT_PARSE_EMISSION: also accept
+ * `material NAME : Emission color r g b;` — MaterialType::Emission exists (materials.rs:11) but
+ * parser.rs:171-174 cannot produce it. */
+#define RT_PARSE_EMISSION 0x1u
+struct Rust_WorldHandle *rt_load_world_ext(const char *source, uint32_t extensions);
+
+/* The inverse of load_world: the world (with its camera as `camera origin .. aspect ..`) in the
+ * grammar of parser.rs:326-335, every float as its exact decimal expansion, so that
+ * load_world(text) reproduces the primitives bit for bit.  Materials of type Emission are written
+ * as `Emission color r g b` (read back with rt_load_world_ext + RT_PARSE_EMISSION).  Returns the size
+ * needed including the terminating NUL (call with buffer = NULL to query); 0 on failure. */
+size_t rt_world_to_text(const struct Rust_WorldHandle *handle, char *buffer, size_t capacity);
+
 /* image.rs:59-81: ASCII PPM (P3), and a binary P6 variant.  Return 0 on success. */
 int rt_write_image(struct Rust_CFramebuffer framebuffer, const char *path);
 int rt_write_image_p6(struct Rust_CFramebuffer framebuffer, const char *path);

@@ -85,14 +85,14 @@ _lib: Optional[C.CDLL] = None
 
 # Every symbol include/raytracer.h and include/raytracer_b200.h declare.
 EXPORTED_SYMBOLS = (
-    "load_world", "render", "move_camera_position",
+    "load_world", "render", "move_camera_position", "rt_load_world_ext",
     "rt_last_error", "rt_abi_version", "rt_device_count", "rt_free_world", "rt_free_camera",
     "render_with_options", "rt_render_device", "rt_shard_pixel_count",
     "rt_set_camera_at", "rt_set_camera_vertical_fov", "rt_set_camera_look_at", "rt_set_camera_raw",
     "rt_get_camera",
     "rt_camera_aspect_ratio", "rt_world_new", "rt_world_add_sphere", "rt_world_add_triangle",
     "rt_world_sphere_count", "rt_world_triangle_count", "rt_world_get_sphere", "rt_world_get_triangle",
-    "rt_write_image", "rt_write_image_p6",
+    "rt_world_to_text", "rt_write_image", "rt_write_image_p6",
     "rt_alloc_pixels", "rt_free_pixels", "rt_measure_fp32_peak", "rt_selftest_division",
     "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_copy_to_host",
 )
@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
     hp = C.POINTER(_WorldHandle)
     L.load_world.restype = hp
     L.load_world.argtypes = [C.c_char_p]
+    L.rt_load_world_ext.restype = hp
+    L.rt_load_world_ext.argtypes = [C.c_char_p, C.c_uint32]
     L.render.restype = _CFramebuffer
     L.render.argtypes = [_CFramebuffer, hp]
     L.move_camera_position.restype = C.c_void_p
@@ -155,6 +157,8 @@ def lib() -> C.CDLL:
     L.rt_world_get_sphere.argtypes = [hp, C.c_size_t, f3]
     L.rt_world_get_triangle.restype = C.c_int
     L.rt_world_get_triangle.argtypes = [hp, C.c_size_t, f3]
+    L.rt_world_to_text.restype = C.c_size_t
+    L.rt_world_to_text.argtypes = [hp, C.c_char_p, C.c_size_t]
     L.rt_write_image.restype = C.c_int
     L.rt_write_image.argtypes = [_CFramebuffer, C.c_char_p]
     L.rt_write_image_p6.restype = C.c_int
@@ -311,6 +315,15 @@ class WorldHandle:
         if lib().rt_world_add_triangle(self.ptr, _f3(v0), _f3(v1), _f3(v2), int(material), _f3(color), float(param)):
             raise RenderError(last_error())
 
+    def to_text(self) -> str:
+        """The world in the reference's text grammar (exact decimal floats; round-trips bit for bit)."""
+        n = lib().rt_world_to_text(self.ptr, None, 0)
+        if not n:
+            raise RenderError(last_error())
+        buf = C.create_string_buffer(n)
+        lib().rt_world_to_text(self.ptr, buf, n)
+        return buf.value.decode("ascii")
+
     # ---- camera (camera.rs:21-72) ----
     def camera_floats(self) -> np.ndarray:
         out = (C.c_float * 12)()
@@ -339,11 +352,15 @@ class WorldHandle:
             raise RenderError(last_error())
 
 
-def load_world(source) -> WorldHandle:
-    """lib.rs:37-46.  Raises ParseError where the reference panics."""
+PARSE_EMISSION = 0x1
+
+
+def load_world(source, extensions: int = 0) -> WorldHandle:
+    """lib.rs:37-46.  Raises ParseError where the reference panics.  extensions=PARSE_EMISSION
+    additionally accepts `material NAME : Emission color r g b;` (rt_load_world_ext)."""
     if isinstance(source, str):
         source = source.encode("utf-8")
-    p = lib().load_world(source)
+    p = lib().rt_load_world_ext(source, int(extensions)) if extensions else lib().load_world(source)
     if not p:
         raise ParseError(last_error())
     return WorldHandle(p)

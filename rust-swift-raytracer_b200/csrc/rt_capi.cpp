@@ -103,12 +103,12 @@ const char* rt_last_error(void) { return g_error.c_str(); }
 uint32_t    rt_abi_version(void) { return RT_B200_ABI_VERSION; }
 int         rt_device_count(void) { return rt::device_count(); }
 
-Rust_WorldHandle* load_world(const char* source)
+static Rust_WorldHandle* load_world_impl(const char* source, bool allow_emission)
 {
     clear_error();
     if (!source) { set_error("load_world: source is NULL"); return nullptr; }
     try {
-        rt::ParseResult r = rt::parse_input(source, std::strlen(source));
+        rt::ParseResult r = rt::parse_input(source, std::strlen(source), allow_emission);
         if (r.error != rt::ParseError::Ok) {
             set_error(std::string("load_world: ParseError: ") + rt::parse_error_name(r.error));
             return nullptr;
@@ -121,6 +121,12 @@ Rust_WorldHandle* load_world(const char* source)
         set_error(e.what());
         return nullptr;
     }
+}
+
+Rust_WorldHandle* load_world(const char* source) { return load_world_impl(source, false); }
+Rust_WorldHandle* rt_load_world_ext(const char* source, uint32_t extensions)
+{
+    return load_world_impl(source, (extensions & RT_PARSE_EMISSION) != 0);
 }
 
 Rust_Camera* move_camera_position(Rust_Camera* camera, float x, float y, float z)
@@ -287,6 +293,18 @@ int rt_world_get_triangle(const Rust_WorldHandle* h, size_t i, float out[18])
                          t.material.r, t.material.g, t.material.b, t.material.param, 0.f};
     std::memcpy(out, v, sizeof v);
     return 0;
+}
+
+size_t rt_world_to_text(const Rust_WorldHandle* h, char* buffer, size_t capacity)
+{
+    size_t need = 0;
+    guarded([&] {
+        if (!h || !h->world || !h->camera) throw std::runtime_error("NULL world handle");
+        const std::string s = rt::world_to_text(*h->world->world, h->camera->camera);
+        need = s.size() + 1;
+        if (buffer && capacity >= need) std::memcpy(buffer, s.c_str(), need);
+    });
+    return need;
 }
 
 static int write_any(Rust_CFramebuffer fb, const char* path, bool p6)

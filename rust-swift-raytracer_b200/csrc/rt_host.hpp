@@ -156,7 +156,12 @@ struct ParseResult {
     std::unique_ptr<World> world;
 };
 // parser.rs:336-382 (source need not be NUL-terminated here)
-ParseResult parse_input(const char* source, size_t length);
+// allow_emission: also accept `material NAME : Emission color r g b;` (an extension; off = the reference's grammar)
+ParseResult parse_input(const char* source, size_t length, bool allow_emission = false);
+
+// The inverse of parse_input: `world` + a new_at camera in the reference's grammar, every float
+// as its exact decimal expansion (parse_input(world_to_text(w)) reproduces w bit for bit).
+std::string world_to_text(const World& world, const Camera& camera);
 
 // common.rs:320-361 on the GPU.  Renders into framebuffer.pixels and returns it.
 // Throws std::runtime_error on any CUDA failure (no CPU fallback exists).

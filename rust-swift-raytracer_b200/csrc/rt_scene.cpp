@@ -269,6 +269,55 @@ const World::Packed& World::packed() const
     return *packed_;
 }
 
+// ----------------------------------------------------------------- world -> text
+// The inverse of parse_input: the world in the reference's grammar (parser.rs:326-335).
+// parse_float accepts only `-?digits[.digits]` (no exponent), so every f32 is printed as its
+// exact finite decimal expansion, which any correctly rounding parser reads back bit for bit.
+namespace {
+void put_float(std::string& out, float v)
+{
+    if (!std::isfinite(v)) v = 0.0f;                       // not expressible in the grammar
+    char buf[512];
+    int n = std::snprintf(buf, sizeof buf, "%.160f", (double)v);   // exact: a float has < 150 fractional digits
+    while (n > 0 && buf[n - 1] == '0') --n;
+    if (n > 0 && buf[n - 1] == '.') { buf[n++] = '0'; }
+    if (n < 3) { buf[n++] = '0'; }                         // parse_float needs >= 3 bytes of input (parser.rs:112-114)
+    out.append(buf, (size_t)n);
+}
+void put_vec(std::string& out, RtVec3 v) { put_float(out, v.x); out += ' '; put_float(out, v.y); out += ' '; put_float(out, v.z); }
+void put_material(std::string& out, size_t index, const Material& m)
+{
+    out += "material M" + std::to_string(index) + " : ";
+    switch (m.type) {
+    case RT_MAT_DIFFUSE:    out += "Diffuse color "; put_vec(out, RtVec3{m.r, m.g, m.b}); break;
+    case RT_MAT_METAL:      out += "Metal color "; put_vec(out, RtVec3{m.r, m.g, m.b}); out += " fuzz "; put_float(out, m.param); break;
+    case RT_MAT_DIELECTRIC: out += "Dielectric ir "; put_float(out, m.param); break;
+    default:                out += "Emission color "; put_vec(out, RtVec3{m.r, m.g, m.b}); break;
+    }
+    out += ";\n";
+}
+}   // namespace
+
+std::string world_to_text(const World& w, const Camera& camera)
+{
+    std::string out;
+    out.reserve(128 * (w.spheres.size() + w.triangles.size()) + 256);
+    // the grammar's camera is Camera::new_at(origin, aspect) (parser.rs:145-167)
+    out += "camera origin "; put_vec(out, camera.d.origin); out += " aspect "; put_float(out, camera.aspect_ratio()); out += ";\n";
+    for (size_t i = 0; i < w.spheres.size(); ++i) put_material(out, i, w.spheres[i].material);
+    for (size_t j = 0; j < w.triangles.size(); ++j) put_material(out, w.spheres.size() + j, w.triangles[j].material);
+    for (size_t i = 0; i < w.spheres.size(); ++i) {
+        out += "sphere center "; put_vec(out, w.spheres[i].center); out += " radius "; put_float(out, w.spheres[i].radius);
+        out += " material M" + std::to_string(i) + ";\n";
+    }
+    for (size_t j = 0; j < w.triangles.size(); ++j) {
+        const Triangle& t = w.triangles[j];
+        out += "triangle v0 "; put_vec(out, t.v0); out += " v1 "; put_vec(out, t.v1); out += " v2 "; put_vec(out, t.v2);
+        out += " material M" + std::to_string(w.spheres.size() + j) + ";\n";
+    }
+    return out;
+}
+
 // ----------------------------------------------------------------- parser.rs
 
 const char* parse_error_name(ParseError e)
@@ -420,7 +469,7 @@ bool statement_camera(Cursor& c, Camera& cam)               // parser.rs:145-167
     return true;
 }
 
-bool statement_material(Cursor& c, MaterialMap& map)        // parser.rs:175-234
+bool statement_material(Cursor& c, MaterialMap& map, bool allow_emission)   // parser.rs:175-234
 {
     if (!c.accept("material")) return false;
     c.skip_whitespace();
@@ -444,6 +493,14 @@ bool statement_material(Cursor& c, MaterialMap& map)        // parser.rs:175-234
         float ir = c.number(); c.skip_whitespace();
         c.expect(";");
         m = Material::Dielectric(ir);
+    } else if (allow_emission && c.accept("Emission")) {
+        // Opt-in extension (rt_load_world_ext): MaterialType::Emission exists
+        // (materials.rs:11) but the reference grammar cannot express it (parser.rs:171-174) —
+        // load_world keeps rejecting it, as the reference does; same shape as Diffuse.
+        c.skip_whitespace(); c.expect("color"); c.skip_whitespace();
+        RtVec3 col = c.vec3(); c.skip_whitespace();
+        c.expect(";");
+        m = Material::Emission(col.x, col.y, col.z);
     } else {
         throw Fail{ParseError::WrongSyntax};
     }
@@ -490,7 +547,7 @@ bool statement_triangle(Cursor& c, const MaterialMap& map, std::vector<Triangle>
 
 }   // namespace
 
-ParseResult parse_input(const char* source, size_t length)
+ParseResult parse_input(const char* source, size_t length, bool allow_emission)
 {
     ParseResult res;
     sv text(source, length);
@@ -505,7 +562,7 @@ ParseResult parse_input(const char* source, size_t length)
         if (!statement_camera(c, res.camera)) throw Fail{ParseError::MissingCamera};
         c.skip_whitespace();
         c.skip_comment();                                                  // :353
-        while (statement_material(c, materials)) { c.skip_whitespace(); c.skip_comment(); }
+        while (statement_material(c, materials, allow_emission)) { c.skip_whitespace(); c.skip_comment(); }
         while (statement_sphere(c, materials, spheres)) { c.skip_whitespace(); c.skip_comment(); }
         while (statement_triangle(c, materials, triangles)) { c.skip_whitespace(); c.skip_comment(); }
         if (!c.s.empty()) throw Fail{ParseError::WrongSyntax};             // :377-378

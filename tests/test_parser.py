@@ -100,3 +100,32 @@ def test_default_world_matches_reference_scene(rt, scenes):
     assert h.n_spheres == 8
     for k, (c, r, t, col, p) in enumerate(want):
         assert np.array_equal(h.sphere(k), np.array([*c, r, t, *col, p], dtype=np.float32))
+
+
+def test_emission_extension_and_world_to_text_round_trip(rt, scenes):
+    """SURVEY.md 8f-1: `Emission color r g b` (MaterialType::Emission exists, materials.rs:11, but the
+    reference grammar cannot express it) and the inverse of load_world with exact decimal floats."""
+    src = scenes.example_world().replace("material GLASS : Dielectric ir 1.5;",
+                                         "material GLASS : Dielectric ir 1.5;\nmaterial LAMP : Emission color 4.0 3.5 0.25;")
+    src = src.replace("radius 0.5 material MIRROR", "radius 0.5 material LAMP")
+    with pytest.raises(rt.ParseError):
+        rt.load_world(src)                               # load_world stays the reference's grammar
+    h = rt.load_world(src, rt.PARSE_EMISSION)
+    assert any(h.sphere(i)[4] == rt.EMISSION and list(h.sphere(i)[5:8]) == [4.0, 3.5, 0.25] for i in range(h.n_spheres))
+    # awkward floats: tiny, huge, negative zero, non-terminating binary fractions
+    g = rt.world_new((0.1, -0.0, 1e-7), 1.77778)
+    g.add_sphere((1e-20, 123456.789, -3.3333333), 0.1, rt.METAL, (0.123456789, 1e-9, 0.999999), 0.3)
+    g.add_sphere((0, 0, -1), 7.5e8, rt.EMISSION, (2, 3, 4))
+    g.add_triangle((0.1, 0.2, 0.3), (1.1, 0.2, 0.3), (0.1, 1.2, 0.35), rt.DIELECTRIC, (1, 1, 1), 1.5)
+    for w in (h, g):
+        text = w.to_text()
+        assert "e" not in text.split("Emission")[0].replace("sphere", "").replace("center", "").replace("triangle", "")\
+            .replace("material", "").replace("Dielectric", "").replace("Metal", "").replace("Diffuse", "").replace("aspect", "")\
+            .replace("camera", "")                                # no exponents anywhere (parse_float has none)
+        w2 = rt.load_world(text, rt.PARSE_EMISSION)
+        assert (w2.n_spheres, w2.n_triangles) == (w.n_spheres, w.n_triangles)
+        for i in range(w.n_spheres):
+            assert w2.sphere(i).tobytes() == w.sphere(i).tobytes()
+        for j in range(w.n_triangles):
+            assert w2.triangle(j).tobytes() == w.triangle(j).tobytes()
+        assert w2.camera_floats().tobytes() == w.camera_floats().tobytes()
