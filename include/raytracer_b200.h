@@ -86,6 +86,17 @@ struct Rust_CFramebuffer render_with_options(struct Rust_CFramebuffer framebuffe
                                              const struct Rust_WorldHandle *handle,
                                              const RtRenderOptions *options);
 
+/* Progressive frame for interactive callers (GameView.swift re-renders on every key press and
+ * idles in between): every call adds options->samples_per_pixel samples to what earlier calls
+ * accumulated for the same world, camera, size, seed, depth and kernel, keeps the float sums in
+ * device memory, and writes the resolved frame; any change of those (camera moved, window
+ * resized, world edited) starts over.  k calls of n spp produce exactly the bits of one call of
+ * k*n spp.  *total_spp_out (optional) receives the samples per pixel in the frame. */
+struct Rust_CFramebuffer rt_render_progressive(struct Rust_CFramebuffer framebuffer,
+                                               const struct Rust_WorldHandle *handle,
+                                               const RtRenderOptions *options, int32_t *total_spp_out);
+void rt_progressive_reset(const struct Rust_WorldHandle *handle);
+
 /* Device-resident variant for multi-GPU plumbing and benchmarks.  device_pixels: RGBA8 in
  * device memory — the full width*height frame when shard_count <= 1, otherwise this shard's
  * tiles packed back to back (rt_shard_pixel_count pixels).  device_accum: optional float4

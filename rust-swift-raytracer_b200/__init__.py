@@ -87,7 +87,7 @@ _lib: Optional[C.CDLL] = None
 EXPORTED_SYMBOLS = (
     "load_world", "render", "move_camera_position", "rt_load_world_ext",
     "rt_last_error", "rt_abi_version", "rt_device_count", "rt_free_world", "rt_free_camera",
-    "render_with_options", "rt_render_device", "rt_shard_pixel_count",
+    "render_with_options", "rt_render_progressive", "rt_progressive_reset", "rt_render_device", "rt_shard_pixel_count",
     "rt_set_camera_at", "rt_set_camera_vertical_fov", "rt_set_camera_look_at", "rt_set_camera_raw",
     "rt_get_camera",
     "rt_camera_aspect_ratio", "rt_world_new", "rt_world_add_sphere", "rt_world_add_triangle",
@@ -126,6 +126,10 @@ def lib() -> C.CDLL:
     L.rt_free_camera.restype = None
     L.render_with_options.restype = _CFramebuffer
     L.render_with_options.argtypes = [_CFramebuffer, hp, C.POINTER(_RenderOptions)]
+    L.rt_render_progressive.restype = _CFramebuffer
+    L.rt_render_progressive.argtypes = [_CFramebuffer, hp, C.POINTER(_RenderOptions), C.POINTER(C.c_int32)]
+    L.rt_progressive_reset.restype = None
+    L.rt_progressive_reset.argtypes = [hp]
     L.rt_render_device.restype = C.c_int
     L.rt_render_device.argtypes = [hp, C.POINTER(_RenderOptions), C.c_size_t, C.c_size_t, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
@@ -398,6 +402,19 @@ def render_with_options(framebuffer: Framebuffer, handle: WorldHandle, options: 
     if err:
         raise RenderError(err)
     return framebuffer
+
+
+def render_progressive(framebuffer: Framebuffer, handle: WorldHandle, options: Options,
+                       stats: Optional[RenderStats] = None) -> int:
+    """rt_render_progressive: adds options.samples_per_pixel samples to the frame accumulated so far
+    (restarts when camera / size / world / seed / depth changed).  Returns the total spp in the frame."""
+    o = options._c(stats)
+    total = C.c_int32(0)
+    lib().rt_render_progressive(framebuffer._c(), handle.ptr, C.byref(o), C.byref(total))
+    err = last_error()
+    if err:
+        raise RenderError(err)
+    return total.value
 
 
 def ray_trace(handle: WorldHandle, framebuffer: Framebuffer, options: Options,

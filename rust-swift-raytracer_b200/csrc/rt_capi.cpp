@@ -10,7 +10,18 @@
 #include <string>
 
 // The opaque ABI types are the C++ host objects.
-struct Rust_World  { std::unique_ptr<rt::World> world; };
+// State of the progressive frame of rt_render_progressive (lives with the world).
+struct Progressive {
+    void*      d_accum = nullptr;      // float4 sums, device memory
+    size_t     cap_px  = 0;
+    int        device  = -1;
+    size_t     width = 0, height = 0;
+    rt::Camera camera{};
+    uint32_t   seed = 0, flags = 0;
+    int32_t    depth = 0;
+    int32_t    done  = 0;              // samples per pixel accumulated so far
+};
+struct Rust_World  { std::unique_ptr<rt::World> world; Progressive progressive; };
 struct Rust_Camera { rt::Camera camera; };
 
 namespace {
@@ -160,6 +171,60 @@ Rust_CFramebuffer render_with_options(Rust_CFramebuffer fb, const Rust_WorldHand
     return fb;
 }
 
+// the interactive caller (GameView.swift re-renders on every key press, and sits
+// idle in between).  Every call adds options->samples_per_pixel samples to the frame accumulated
+// so far for the same world, camera, size, seed and depth — the sums stay in device memory, the
+// sample indices continue where the last call stopped, so k calls of n spp give exactly the
+// bits of one call of k*n spp — and starts over when any of those changed (camera moved,
+// window resized, world edited).
+Rust_CFramebuffer rt_render_progressive(Rust_CFramebuffer fb, const Rust_WorldHandle* handle,
+                                        const RtRenderOptions* options, int32_t* total_spp_out)
+{
+    if (total_spp_out) *total_spp_out = 0;
+    guarded([&] {
+        if (!handle || !handle->world || !handle->camera) throw std::runtime_error("rt_render_progressive: NULL world handle");
+        if (!fb.pixels) throw std::runtime_error("rt_render_progressive: framebuffer.pixels is NULL");
+        rt::Options  o = to_options(options);
+        Progressive& p = handle->world->progressive;
+        if (o.samples_per_pixel < 1) throw std::runtime_error("rt_render_progressive: samples_per_pixel must be >= 1");
+        if (o.shard_count > 1 || o.n_devices > 1) throw std::runtime_error("rt_render_progressive: single device only");
+        const uint32_t key_flags = (o.fixed_jitter ? 1u : 0u) | (o.fast_math ? 2u : 0u);
+        const bool same = p.d_accum && p.width == fb.width && p.height == fb.height && p.seed == o.seed &&
+                          p.depth == o.max_ray_bounces && p.flags == key_flags && p.device == o.device &&
+                          std::memcmp(&p.camera.d, &handle->camera->camera.d, sizeof p.camera.d) == 0;
+        if (!same) {
+            const size_t px = fb.width * fb.height;
+            if (p.cap_px < px || p.device != o.device) {
+                if (p.d_accum) rt::device_free(p.d_accum);
+                p.d_accum = nullptr; p.cap_px = 0;
+                p.d_accum = rt::device_alloc(px * 4 * sizeof(float));
+                p.cap_px  = px;
+            }
+            p.width = fb.width; p.height = fb.height; p.seed = o.seed; p.depth = o.max_ray_bounces;
+            p.flags = key_flags; p.device = o.device; p.camera = handle->camera->camera; p.done = 0;
+        }
+        rt::RenderStats st;
+        RtRenderStats*  out_stats = (options && options->struct_size >= sizeof(RtRenderOptions)) ? options->stats : nullptr;
+        if (out_stats) o.stats = &st;
+        o.sample_begin = p.done;
+        o.resolve_spp  = p.done + o.samples_per_pixel;
+        o.accum_in     = p.done > 0;
+        o.accum_out    = true;
+        o.no_resolve   = false;
+        rt::ray_trace_into(*handle->world->world, handle->camera->camera, fb.width, fb.height, o,
+                           reinterpret_cast<rt::ColorU8*>(fb.pixels), nullptr, p.d_accum, nullptr);
+        p.done += o.samples_per_pixel;
+        if (total_spp_out) *total_spp_out = p.done;
+        if (out_stats) export_stats(st, out_stats);
+    });
+    return fb;
+}
+
+void rt_progressive_reset(const Rust_WorldHandle* handle)
+{
+    if (handle && handle->world) handle->world->progressive.done = 0, handle->world->progressive.width = 0;
+}
+
 Rust_CFramebuffer render(Rust_CFramebuffer fb, const Rust_WorldHandle* handle)
 {
     return render_with_options(fb, handle, nullptr);   // Options::new(16, 8, None, true), lib.rs:51
@@ -192,6 +257,7 @@ size_t rt_shard_pixel_count(size_t width, size_t height, uint32_t tile_rows, uin
 void rt_free_world(Rust_WorldHandle* h)
 {
     if (!h) return;
+    if (h->world && h->world->progressive.d_accum) rt::device_free(h->world->progressive.d_accum);
     delete h->world;
     delete h->camera;
     delete h;
@@ -258,6 +324,7 @@ int rt_world_add_sphere(Rust_WorldHandle* h, const float center[3], float radius
         h->world->world->spheres.push_back(rt::Sphere{RtVec3{center[0], center[1], center[2]}, radius,
                                                       make_material(material, color, param)});
         h->world->world->invalidate_device();
+        rt_progressive_reset(h);
     });
 }
 int rt_world_add_triangle(Rust_WorldHandle* h, const float v0[3], const float v1[3], const float v2[3],
@@ -270,6 +337,7 @@ int rt_world_add_triangle(Rust_WorldHandle* h, const float v0[3], const float v1
                                                                 RtVec3{v2[0], v2[1], v2[2]},
                                                                 make_material(material, color, param)));
         h->world->world->invalidate_device();
+        rt_progressive_reset(h);
     });
 }
 size_t rt_world_sphere_count(const Rust_WorldHandle* h) { return (h && h->world) ? h->world->world->spheres.size() : 0; }

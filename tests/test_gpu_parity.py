@@ -275,6 +275,30 @@ def test_pinned_and_pageable_destinations_agree(gpu_rt, scenes):
     assert np.array_equal(a, b)
 
 
+def test_interactive_progressive_frame(gpu_rt, ob, scenes):
+    """rt_render_progressive: 5 calls of 3 spp == one 15-spp frame bit for bit; a
+    camera move (GameView.swift:198-216) or a resize restarts the accumulation."""
+    rt = gpu_rt
+    W, H = 160, 90
+    h = rt.load_world(scenes.default_world())
+    cam, world = ob.parse_input(scenes.default_world())
+    fb = rt.Framebuffer(W, H)
+    for k in range(5):
+        assert rt.render_progressive(fb, h, rt.Options(3, 8)) == 3 * (k + 1)
+        want, _, _ = ob.ray_trace(world, cam, W, H, 3 * (k + 1), 8)
+        assert np.array_equal(fb.pixels, want), k
+    rt.move_camera_position(h, 0.25, 0.0, 0.0)
+    cam = ob.move_camera_position(cam, 0.25, 0.0, 0.0)
+    assert rt.render_progressive(fb, h, rt.Options(2, 8)) == 2
+    want, _, _ = ob.ray_trace(world, cam, W, H, 2, 8)
+    assert np.array_equal(fb.pixels, want)
+    fb2 = rt.Framebuffer(W // 2, H // 2)
+    assert rt.render_progressive(fb2, h, rt.Options(1, 8)) == 1
+    assert rt.render_progressive(fb2, h, rt.Options(4, 8)) == 5
+    want, _, _ = ob.ray_trace(world, cam, W // 2, H // 2, 5, 8)
+    assert np.array_equal(fb2.pixels, want)
+
+
 def test_errors_do_not_cross_the_abi(gpu_rt, scenes):
     rt = gpu_rt
     h = rt.load_world(scenes.default_world())
