@@ -1,4 +1,4 @@
-"""Small renders covering every kernel variant, for `compute-sanitizer --tool memcheck` (one tool per call)."""
+"""Small renders covering every kernel variant, every kernel variant once (compute-sanitizer is closed on this pool, so this is a plain smoke)."""
 import importlib, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
