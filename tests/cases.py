@@ -47,3 +47,67 @@ def product_scene(rt, scenes, key, camera):
     if camera != "file":
         h.set_camera_look_at(*camera)
     return h
+
+
+# ---- random worlds for fuzzing the conservative filters (spheres / triangle plane + edge stages) ----
+
+def random_world(seed: int, n_spheres: int = 70, n_triangles: int = 12) -> str:
+    """A world text with awkward geometry: radii over six decades, far-away and huge primitives,
+    spheres containing the camera, needle-thin / degenerate / far-from-origin triangles.
+    >= 64 spheres so that the FILTER kernels run."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+
+    def f(v):
+        s = f"{float(v):.6f}"
+        return "0.000000" if s == "-0.000000" else s
+
+    lines = [f"camera origin {f(rng.uniform(-1, 1))} {f(rng.uniform(-0.5, 1))} {f(rng.uniform(-1, 1))} aspect 1.5;"]
+    mats = []
+    for i in range(8):
+        k = rng.integers(0, 3)
+        c = rng.uniform(0.05, 1.0, 3)
+        if k == 0:
+            mats.append(f"material M{i} : Diffuse color {f(c[0])} {f(c[1])} {f(c[2])};")
+        elif k == 1:
+            mats.append(f"material M{i} : Metal color {f(c[0])} {f(c[1])} {f(c[2])} fuzz {f(rng.choice([0.0, 0.1, 0.5, 1.0]))};")
+        else:
+            mats.append(f"material M{i} : Dielectric ir {f(rng.choice([1.0, 1.33, 1.5, 2.4]))};")
+    lines += mats
+    for i in range(n_spheres):
+        kind = rng.integers(0, 10)
+        if kind == 0:      # huge, far below (ground-like)
+            r = 10.0 ** rng.uniform(1, 4)
+            c = (rng.uniform(-5, 5), -r - rng.uniform(0.3, 1.0), rng.uniform(-5, 5))
+        elif kind == 1:    # tiny
+            r = 10.0 ** rng.uniform(-3, -1.5)
+            c = rng.uniform(-2, 2, 3) + np.array([0, 0, -3.0])
+        elif kind == 2:    # far away
+            r = rng.uniform(5, 50)
+            c = rng.uniform(-1, 1, 3) * 10.0 ** rng.uniform(2, 3.5)
+        elif kind == 3:    # contains the camera
+            r = rng.uniform(3, 30)
+            c = rng.uniform(-1, 1, 3)
+        else:
+            r = rng.uniform(0.05, 0.8)
+            c = rng.uniform(-4, 4, 3) + np.array([0, 0, -5.0])
+        lines.append(f"sphere center {f(c[0])} {f(c[1])} {f(c[2])} radius {f(r)} material M{rng.integers(0, 8)};")
+    for j in range(n_triangles):
+        kind = rng.integers(0, 6)
+        base = rng.uniform(-3, 3, 3) + np.array([0, 0, -4.0])
+        if kind == 0:      # needle: two vertices almost coincide
+            v = [base, base + rng.uniform(-2, 2, 3), None]
+            v[2] = v[1] + rng.uniform(-1, 1, 3) * 1e-4
+        elif kind == 1:    # degenerate: collinear
+            d = rng.uniform(-1, 1, 3)
+            v = [base, base + d, base + 2.0 * d]
+        elif kind == 2:    # large
+            v = [base + rng.uniform(-30, 30, 3) for _ in range(3)]
+        elif kind == 3:    # far from the origin
+            far = base * 10.0 ** rng.uniform(1.5, 3)
+            v = [far + rng.uniform(-1, 1, 3) for _ in range(3)]
+        else:
+            v = [base + rng.uniform(-0.7, 0.7, 3) for _ in range(3)]
+        lines.append("triangle " + " ".join(f"v{k} {f(v[k][0])} {f(v[k][1])} {f(v[k][2])}" for k in range(3)) +
+                     f" material M{rng.integers(0, 8)};")
+    return "\n".join(lines) + "\n"

@@ -178,6 +178,21 @@ def test_empty_world_is_sky(gpu_rt, ob):
     assert st.rays == rays == 64 * 40 * 3 and np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("RT_FUZZ_SEEDS", "24"))))
+def test_random_worlds_fuzz(gpu_rt, ob, seed):
+    """Awkward random geometry through every conservative filter (cases.random_world): bit-exact
+    against the oracle's plain loops, pixel-item and sample-item scheduling alike."""
+    rt = gpu_rt
+    text = cases.random_world(seed)
+    cam, world = ob.parse_input(text)
+    W, H, spp, depth = 96, 64, 3, 8
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    h = rt.load_world(text)
+    for items in (False, True):
+        got, st = _render(rt, h, W, H, spp, depth, sample_items=items)
+        assert st.filtered == 1 and st.rays == rays and np.array_equal(got, want), (seed, items)
+
+
 def test_seed_changes_the_realisation_and_matches_oracle(gpu_rt, ob, scenes):
     rt = gpu_rt
     h = rt.load_world(scenes.default_world())

@@ -55,6 +55,26 @@ def test_filter_variant_of_the_exact_policy_equals_oracle(hostsim, ob, scenes, k
     assert np.array_equal(out, want)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_worlds_through_the_filters(hostsim, ob, seed):
+    """Fuzz: awkward geometry (six decades of radii, far-away / huge / camera-containing spheres,
+    needle / degenerate / distant triangles) through the conservative sphere filter, the triangle
+    plane prefilter and the barycentric edge reject — every pixel and the ray count must equal
+    the oracle's plain loops."""
+    text = cases.random_world(seed)
+    cam, world = ob.parse_input(text)
+    W, H, spp, depth = 40, 28, 2, 6
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    cf = cam.floats()
+    for flags in (0, 0x80000000):                     # direct loops, FILTER variant
+        out = np.zeros((H, W, 4), np.uint8)
+        n = C.c_uint64()
+        rc = hostsim.hostsim_render(text.encode(), cf.ctypes.data_as(C.POINTER(C.c_float)), W, H, spp, depth,
+                                    ob.SEED_DEFAULT, flags, 0, 0, out.ctypes.data, C.byref(n))
+        assert rc == 0 and n.value == rays, (seed, flags)
+        assert np.array_equal(out, want), (seed, flags)
+
+
 @pytest.mark.parametrize("W,H,spp,depth", [(1, 1, 2, 4), (2, 2, 1, 8), (5, 3, 0, 8), (5, 3, 2, 0), (7, 1, 1, 3), (1, 9, 1, 3)])
 def test_degenerate_frames(hostsim, ob, scenes, W, H, spp, depth):
     """W or H of 1 divides by zero in common.rs:335-336 (NaN rays -> black), spp 0 resolves 0/0,
