@@ -332,7 +332,8 @@ def main():
             tot += allreduce(time.perf_counter() - t0, dist.ReduceOp.MAX if n_gpus > 1 else None)
         e2e = {"value": rays_frame / (tot / args.steps) / 1e6, "unit": "Mrays/s",
                "ms_per_frame": tot / args.steps * 1e3,
-               "h2d_bytes_per_step": 184 * passes,      # camera + frame parameters travel as kernel arguments;
+               "h2d_bytes_per_step": 232 * passes,      # camera + frame parameters travel as kernel arguments
+               # (sizeof RtFrameParams + RtSceneView = 160 + 72);
                # the scene blob is uploaded once by load_world (the reference's API has the same split)
                "d2h_bytes_per_step": W * H * 4,
                "api": "render_with_options (C ABI, pinned host framebuffer)" if (n_gpus == 1 and passes == 1)

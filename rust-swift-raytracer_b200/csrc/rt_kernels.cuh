@@ -129,9 +129,12 @@ __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_
 #ifndef RT_MIN_CTAS_SMALL
 #define RT_MIN_CTAS_SMALL 4   // 256-thread CTAs per SM the register allocation must allow (<= 64 registers)
 #endif
+#ifndef RT_MIN_CTAS_FILTER
+#define RT_MIN_CTAS_FILTER 3  // FILTER kernels: 80 registers measured faster than 64 (the loop is FFMA-bound,
+#endif                        // not latency-bound: C3 fast 399 -> 369 ms, exact 439 -> 431 ms)
 
 template <bool FAST, bool SMEM, int BLOCK, bool FILTER, bool TRIS>
-__global__ void __launch_bounds__(BLOCK, BLOCK == 256 ? RT_MIN_CTAS_SMALL : 1) rt_render_kernel(const __grid_constant__ RtFrameParams P,
+__global__ void __launch_bounds__(BLOCK, BLOCK != 256 ? 1 : FILTER ? RT_MIN_CTAS_FILTER : RT_MIN_CTAS_SMALL) rt_render_kernel(const __grid_constant__ RtFrameParams P,
                                                          const __grid_constant__ RtSceneView  G)
 {
     extern __shared__ __align__(128) unsigned char rt_smem[];
@@ -292,7 +295,10 @@ cudaError_t launch_resolve_samples(const RtFrameParams& P, cudaStream_t stream)
 // a list that fills most of shared memory (thousands of primitives) allows only one CTA
 // per SM, which then has to be 1024 threads wide to keep the SM's schedulers fed.
 constexpr int      kBlockSmall    = 256;
-constexpr int      kBlockLarge    = 1024;
+#ifndef RT_BLOCK_LARGE
+#define RT_BLOCK_LARGE 1024
+#endif
+constexpr int      kBlockLarge    = RT_BLOCK_LARGE;
 constexpr size_t   kLargeSmemFrom = 56 * 1024;   // above this, < 4 CTAs of 256 threads would fit
 constexpr uint32_t kFilterFrom    = 64;          // spheres from which the kernels filter first
 
