@@ -314,6 +314,35 @@ def test_interactive_progressive_frame(gpu_rt, ob, scenes):
     assert np.array_equal(fb2.pixels, want)
 
 
+def test_concurrent_callers_are_serialised(gpu_rt, scenes):
+    """The reference is single-threaded; the library guards its device state with one mutex, so
+    threads rendering different worlds at the same time get the frames they would get alone."""
+    import threading
+    rt = gpu_rt
+    jobs = [(scenes.default_world(), 160, 90, 4), (scenes.example_world(), 120, 120, 3), (scenes.c3_world(), 48, 27, 1)]
+    alone = []
+    for text, W, H, spp in jobs:
+        got, _ = _render(rt, rt.load_world(text), W, H, spp, 8)
+        alone.append(got)
+    results = [None] * len(jobs)
+
+    def work(i):
+        text, W, H, spp = jobs[i]
+        h = rt.load_world(text)
+        for _ in range(5):
+            fb = rt.Framebuffer(W, H)
+            rt.lib().render_with_options(fb._c(), h.ptr, rt.Options(spp, 8)._c(None))
+            results[i] = fb.pixels.copy()
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for got, want in zip(results, alone):
+        assert np.array_equal(got, want)
+
+
 def test_errors_do_not_cross_the_abi(gpu_rt, scenes):
     rt = gpu_rt
     h = rt.load_world(scenes.default_world())
