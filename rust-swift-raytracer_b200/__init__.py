@@ -498,8 +498,21 @@ def selftest_division(operand_sets: int = 1 << 28, seed: int = 1, device: int = 
 
 # ---- shard geometry shared by the multi-GPU plumbing (tile t belongs to rank t % N) ----
 
+def shard_tile(shard_index: int, shard_count: int, j: int) -> int:
+    """rt_shard_tile (rt_types.h): stripes of shard_count tiles are dealt alternately forwards and
+    backwards, so that a vertical cost gradient of the frame cancels between the shards."""
+    return j * shard_count + ((shard_count - 1 - shard_index) if (j & 1) else shard_index)
+
+
 def shard_tiles(height: int, tile_rows: int, shard_index: int, shard_count: int):
     """Image-row ranges [(r0, r1), ...] of the tiles shard `shard_index` renders, in the order
     they are packed in its compact buffer."""
     n_tiles = (height + tile_rows - 1) // tile_rows
-    return [(t * tile_rows, min((t + 1) * tile_rows, height)) for t in range(shard_index, n_tiles, shard_count)]
+    out, j = [], 0
+    while True:
+        t = shard_tile(shard_index, shard_count, j)
+        if t >= n_tiles:
+            # a later stripe cannot contain a tile either: stripes are whole multiples of shard_count
+            return out
+        out.append((t * tile_rows, min((t + 1) * tile_rows, height)))
+        j += 1

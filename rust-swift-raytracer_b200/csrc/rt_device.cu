@@ -339,7 +339,7 @@ uint64_t shard_pixels(uint32_t W, uint32_t H, const Options& opt, uint32_t n_til
 {
     uint64_t px = 0;
     for (uint32_t j = 0; j < n_tiles; ++j) {
-        const uint64_t tile = (uint64_t)opt.shard_index + (uint64_t)j * opt.shard_count;
+        const uint64_t tile = rt_shard_tile(opt.shard_index, opt.shard_count, j);
         const uint64_t r0   = tile * opt.tile_rows;
         const uint64_t r1   = std::min<uint64_t>(r0 + opt.tile_rows, H);
         px += (r1 - r0) * W;
@@ -389,7 +389,7 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
         auto for_each_piece = [&](auto&& f) {
             if (opt.shard_count <= 1) { f((size_t)0, (size_t)0, (size_t)W * H); return; }
             for (uint32_t j = 0; j < n_tiles; ++j) {
-                const size_t tile  = (size_t)opt.shard_index + (size_t)j * opt.shard_count;
+                const size_t tile  = rt_shard_tile(opt.shard_index, opt.shard_count, j);
                 const size_t first = tile * tile_px;
                 const size_t count = std::min(tile_px, (size_t)W * H - first);
                 f(first, L.compact ? (size_t)j * tile_px : first, count);
@@ -504,7 +504,7 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
         if (!peer && launches[d].n_tiles > 0) {        // fallback gather: D2H tile by tile from every device
             if (!direct) ensure_stage(*ctxs[d], launches[d].out_pixels * 4);
             for (uint32_t j = 0; j < launches[d].n_tiles; ++j) {
-                const size_t first = ((size_t)d + (size_t)j * N) * tile_px;
+                const size_t first = (size_t)rt_shard_tile((uint32_t)d, (uint32_t)N, j) * tile_px;
                 const size_t count = std::min(tile_px, (size_t)W * H - first);
                 void* dst = direct ? (void*)(host32 + first) : (void*)(ctxs[d]->h_stage + (size_t)j * tile_px * 4);
                 RT_CUDA(cudaMemcpyAsync(dst, launches[d].d_out + (size_t)j * tile_px, count * 4, cudaMemcpyDeviceToHost,
@@ -518,7 +518,7 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
         RT_CUDA(cudaStreamSynchronize(ctxs[d]->stream));
         if (!peer && !direct)
             for (uint32_t j = 0; j < launches[d].n_tiles; ++j) {
-                const size_t first = ((size_t)d + (size_t)j * N) * tile_px;
+                const size_t first = (size_t)rt_shard_tile((uint32_t)d, (uint32_t)N, j) * tile_px;
                 const size_t count = std::min(tile_px, (size_t)W * H - first);
                 std::memcpy(host32 + first, ctxs[d]->h_stage + (size_t)j * tile_px * 4, count * 4);
             }

@@ -116,7 +116,7 @@ __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_
     const uint32_t sx    = c - sy * subtiles_x;
     const uint32_t x     = sx * 8u + (in & 7u);
     const uint32_t yin   = sy * 4u + (in >> 3);
-    const uint32_t tile  = P.tile_first + strip * P.tile_stride;
+    const uint32_t tile  = rt_shard_tile(P.tile_first, P.tile_stride, strip);
     PixelSlot s;
     s.column    = x;
     s.image_row = tile * P.tile_rows + yin;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) rt_resolve_samples_kernel(const __grid_co
     if (local >= rows_out * P.width) return;
     const uint32_t r = local / P.width, x = local - r * P.width;
     const uint32_t strip = r / P.tile_rows, yin = r - strip * P.tile_rows;
-    const uint32_t image_row = (P.tile_first + strip * P.tile_stride) * P.tile_rows + yin;
+    const uint32_t image_row = rt_shard_tile(P.tile_first, P.tile_stride, strip) * P.tile_rows + yin;
     if (image_row >= P.height) return;
     const uint32_t out_row = (P.flags & RT_FLAG_COMPACT_OUT) ? r : image_row;
     const uint32_t idx     = out_row * P.width + x;

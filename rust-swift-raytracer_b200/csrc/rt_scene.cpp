@@ -609,9 +609,12 @@ bool write_image_p6(const Framebuffer& fb, const char* path)
 
 uint32_t shard_tile_count(uint32_t height, uint32_t tile_rows, uint32_t index, uint32_t count)
 {
+    // full stripes of `count` tiles give every shard one tile; in the last, partial stripe a shard
+    // has a tile when its (boustrophedon) position lies inside the remainder — rt_shard_tile
     const uint32_t tiles = (height + tile_rows - 1) / tile_rows;
-    if (index >= tiles) return 0;
-    return (tiles - index + count - 1) / count;
+    const uint32_t full  = tiles / count, rem = tiles % count;
+    const uint32_t pos   = (full & 1u) ? count - 1u - index : index;
+    return full + (pos < rem ? 1u : 0u);
 }
 
 }   // namespace rt

@@ -75,6 +75,20 @@ struct RtSceneView {
     uint32_t          n_tri_pad;  // multiple of RT_TRI_GROUP
 };
 
+// Row-tile sharding.  The frame's tiles (tile_rows image rows each, top to bottom) are dealt to
+// the shards in stripes of `count` consecutive tiles, alternately forwards and backwards
+// (boustrophedon): the j-th tile of shard `index` is tile j*count + (j even ? index : count-1-index).
+// A plain round-robin gives the last shard the lowest tile of EVERY stripe, and cost grows
+// towards the ground: measured 17 % spread between 8 GPUs on C4; the alternation cancels the
+// gradient.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t rt_shard_tile(uint32_t index, uint32_t count, uint32_t j)
+{
+    return j * count + ((j & 1u) ? count - 1u - index : index);
+}
+
 // Flags of RtFrameParams::flags
 enum : uint32_t {
     RT_FLAG_FIXED_JITTER = 1u << 0,   // sub-pixel offset (0.5, 0.5); no jitter draws
@@ -98,7 +112,7 @@ struct RtFrameParams {
     uint32_t seed;
     uint32_t flags;
     // Row-tile sharding: this launch renders image-row tiles
-    //   tile_first, tile_first + tile_stride, ...   (n_tiles of them, tile_rows rows each).
+    //   rt_shard_tile(tile_first, tile_stride, j), j = 0 .. n_tiles-1   (tile_rows rows each).
     uint32_t tile_rows, tile_first, tile_stride, n_tiles;
     uint32_t reserve;        // pixel slots a warp takes per atomicAdd (multiple of 32)
     uint32_t pad0;

@@ -1,11 +1,12 @@
 """Multi-GPU plumbing of the render path: one process per GPU, the frame sharded by row
 tiles, one collective (the gather of finished RGBA8 tiles to rank 0).
 
-Decomposition: the frame is cut into tiles of `tile_rows` image rows; tile t
-belongs to rank t % world (static interleave: sky-heavy and geometry-heavy tiles alternate
-across ranks).  Every tile is one contiguous byte range of the row-major frame (image.rs:27),
-so a rank's output is its tiles packed back to back ("compact" buffer, RT_FLAG_COMPACT_OUT)
-and the gather is a pure data movement: no pixel is touched by more than one rank and no
+Decomposition: the frame is cut into tiles of `tile_rows` image rows, dealt to the
+ranks in stripes of `world` consecutive tiles, alternately forwards and backwards (rt_shard_tile,
+rt_types.h) so that the frame's vertical cost gradient (sky above, ground below) cancels between
+the ranks.  Every tile is one contiguous byte range of the row-major frame (image.rs:27), so a
+rank's output is either its tiles packed back to back ("compact" buffer, RT_FLAG_COMPACT_OUT) or
+stores into the full frame at the tiles' offsets; no pixel is touched by more than one rank and no
 float accumulator ever crosses NVLink.
 
 torch.distributed is plumbing here (NCCL on the GPUs, gloo in the CPU tests); nothing in this
@@ -24,8 +25,11 @@ def tiles_total(height: int, tile_rows: int) -> int:
 
 
 def tiles_of_rank(height: int, tile_rows: int, rank: int, world: int) -> int:
+    """Tiles of `rank` under the boustrophedon dealing of rt_shard_tile (rt_types.h)."""
     t = tiles_total(height, tile_rows)
-    return 0 if rank >= t else (t - rank + world - 1) // world
+    full, rem = divmod(t, world)
+    pos = (world - 1 - rank) if (full & 1) else rank
+    return full + (1 if pos < rem else 0)
 
 
 def compact_pixels(width: int, height: int, tile_rows: int, rank: int, world: int) -> int:
@@ -60,8 +64,11 @@ def gather_frame(local: torch.Tensor, width: int, height: int, tile_rows: int, r
         if staging is None:
             staging = torch.empty((world, j * tile_px), dtype=local.dtype, device=local.device)
         dist.gather(local, gather_list=list(staging.unbind(0)), dst=dst, group=group)
-        # staging[r, jj] is tile jj*world + r  ->  frame order is [jj][r]
-        frame = staging.view(world, j, tile_px).permute(1, 0, 2).reshape(-1)[: width * height]
+        # staging[r, jj] is tile jj*world + (r if jj is even else world-1-r) (rt_shard_tile): frame order is
+        # [jj][r], with the rank axis reversed in the odd stripes
+        tiles = staging.view(world, j, tile_px).permute(1, 0, 2).clone()
+        tiles[1::2] = tiles[1::2].flip(1)
+        frame = tiles.reshape(-1)[: width * height]
         return frame.view(height, width)
     dist.gather(local, gather_list=None, dst=dst, group=group)
     return None
