@@ -299,9 +299,6 @@ def main():
         t_wall = time.perf_counter() - t_wall
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     dev_ms = allreduce(dev_ms, dist.ReduceOp.MAX if n_gpus > 1 else None)
-    own_ms = renderer.own_kernel_ms()              # last step, this rank's kernels only: balance of the tile split
-    own_ms_min = allreduce(own_ms, dist.ReduceOp.MIN if n_gpus > 1 else None)
-    own_ms_max = allreduce(own_ms, dist.ReduceOp.MAX if n_gpus > 1 else None)
     ms_per_step = dev_ms / args.steps
     value = rays_frame / (ms_per_step * 1e-3) / 1e6
 
@@ -376,7 +373,7 @@ def main():
                    if n_gpus > 1 else "1 GPU",
                    "l2": "flushed between steps (256 MiB write, outside the CUDA events)",
                    "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
-                   "rank_own_kernel_ms_min_max": [own_ms_min, own_ms_max]},
+                   },
         "e2e": e2e,
         "gpu_launches": args.steps * passes,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak * n_gpus, "unit": "TFLOP/s",

@@ -102,7 +102,6 @@ class ShardedRenderer:
         assert self.gather in ("peer", "nccl")
         self.accum: Optional[torch.Tensor] = None
         self.host_frame = (torch.empty((height, width), dtype=torch.int32).pin_memory() if rank == 0 else None)
-        self._ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         self.frame_ptr = 0        # peer mode: rank 0's frame (own allocation on rank 0, IPC mapping elsewhere)
         self._owns_frame = False
         if self.gather == "peer" and world > 1:
@@ -124,12 +123,6 @@ class ShardedRenderer:
             j = padded_tiles_per_rank(height, tile_rows, world)
             self.staging = (torch.empty((world, j * tile_rows * width), dtype=torch.int32, device=self.device)
                             if (world > 1 and rank == 0) else None)
-
-    def own_kernel_ms(self) -> float:
-        """Device time of this rank's render kernels in the last render() (excludes the gather /
-        fence, i.e. the time spent waiting for slower ranks).  Synchronises."""
-        self._ev[1].synchronize()
-        return self._ev[0].elapsed_time(self._ev[1])
 
     def close(self):
         if self.frame_ptr:
@@ -159,7 +152,6 @@ class ShardedRenderer:
         stream = tstream.cuda_stream
         out_ptr = self.frame_ptr if peer else self.local.data_ptr()
         per, rays = spp // passes, 0
-        self._ev[0].record(tstream)
         for p in range(passes):
             last = p == passes - 1
             o = rt.Options(per, depth, sample_begin=p * per, resolve_spp=spp, fast_math=fast_math,
@@ -173,7 +165,6 @@ class ShardedRenderer:
                              self.accum.data_ptr() if self.accum is not None else 0, stream, st)
             if st is not None:
                 rays += st.rays
-        self._ev[1].record(tstream)            # this rank's own kernels, before any wait for the others
         if peer:
             # stream-ordered completion fence: rank 0's all-reduce kernel cannot finish before every
             # rank has launched its own, i.e. before every rank's render kernels have completed
