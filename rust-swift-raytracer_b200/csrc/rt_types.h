@@ -79,8 +79,8 @@ struct RtSceneView {
 // the shards in stripes of `count` consecutive tiles, alternately forwards and backwards
 // (boustrophedon): the j-th tile of shard `index` is tile j*count + (j even ? index : count-1-index).
 // A plain round-robin gives the last shard the lowest tile of EVERY stripe, and cost grows
-// towards the ground: measured 17 % spread between 8 GPUs on C4; the alternation cancels the
-// gradient.
+// towards the ground; the alternation cancels such a gradient to first order.  (Measured on C4,
+// 4 GPUs: 131.4-135.8 ms per rank for the 16 passes, the spread being the one tile rank 0 has less.)
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
