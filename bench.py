@@ -333,7 +333,8 @@ def main():
                # (sizeof RtFrameParams + RtSceneView = 160 + 72);
                # the scene blob is uploaded once by load_world (the reference's API has the same split)
                "d2h_bytes_per_step": W * H * 4,
-               "api": "render_with_options (C ABI, pinned host framebuffer)" if (n_gpus == 1 and passes == 1)
+               "api": "render_with_options (C ABI, pinned host framebuffer: the kernel stores the finished pixels "
+                      "straight into it over PCIe, no separate D2H copy)" if (n_gpus == 1 and passes == 1)
                       else f"multi.ShardedRenderer.render(to_host=True): tile shards -> {renderer.gather} gather -> D2H on rank 0"}
 
     one_process = None

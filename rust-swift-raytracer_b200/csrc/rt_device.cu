@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -152,6 +153,17 @@ const DeviceScene& device_scene(const World& w, DeviceContext& ctx)
     s->view = p.view(s->blob);
     w.device_.push_back(std::move(s));
     return *w.device_.back();
+}
+
+// Device-side address of a pinned (page-locked, mapped) host allocation, or nullptr.
+void* mapped_device_pointer(const void* p)
+{
+    static const bool enabled = [] { const char* e = std::getenv("RT_ZERO_COPY"); return !(e && *e == '0'); }();
+    if (!enabled) return nullptr;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
 bool is_pinned_or_device_accessible(const void* p)
@@ -373,12 +385,21 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
     cudaStream_t       stream = user_stream ? static_cast<cudaStream_t>(user_stream) : ctx.stream;
 
     const uint32_t W = (uint32_t)width, H = (uint32_t)height;
-    const ShardLaunch L = enqueue_shard(ctx, scene, camera, W, H, opt, static_cast<uint32_t*>(device_pixels),
+    // Pinned destination (rt_alloc_pixels, cudaHostRegister): the kernel stores every finished
+    // pixel straight into the caller's frame over PCIe (mapped host memory) — 4 B per pixel spread
+    // over the whole render, so no D2H copy follows the kernel.
+    void* zero_copy = (host_pixels && !device_pixels && !opt.no_resolve) ? mapped_device_pointer(host_pixels) : nullptr;
+    Options       zc_opt = opt;
+    if (zero_copy) zc_opt.full_frame_out = true;            // tiles land at their frame offsets
+    const ShardLaunch L = enqueue_shard(ctx, scene, camera, W, H, zero_copy ? zc_opt : opt,
+                                        zero_copy ? static_cast<uint32_t*>(zero_copy) : static_cast<uint32_t*>(device_pixels),
                                         device_accum, stream, opt.stats != nullptr);
     const uint32_t n_tiles = L.n_tiles;
     uint32_t*      d_out   = L.d_out;
 
-    if (host_pixels && !opt.no_resolve && n_tiles > 0) {
+    if (zero_copy) {
+        RT_CUDA(cudaStreamSynchronize(stream));
+    } else if (host_pixels && !opt.no_resolve && n_tiles > 0) {
         // D2H of the finished RGBA8 rows.  Every tile is one contiguous byte range of the frame
         // (image.rs:27 row-major), so a shard copies tile by tile and a full frame in one piece.
         const bool   direct  = is_pinned_or_device_accessible(host_pixels);
