@@ -300,7 +300,7 @@ constexpr int      kBlockSmall    = 256;
 #endif
 constexpr int      kBlockLarge    = RT_BLOCK_LARGE;
 constexpr size_t   kLargeSmemFrom = 56 * 1024;   // above this, < 4 CTAs of 256 threads would fit
-constexpr uint32_t kFilterFrom    = 64;          // spheres from which the kernels filter first
+constexpr uint32_t kFilterFrom    = RT_FILTER_FROM;   // spheres from which the kernels filter first
 
 struct RenderVariant { bool smem; int block; bool filter; bool tris; size_t hot_bytes; };
 

@@ -207,7 +207,7 @@ const World::Packed& World::packed() const
     if (packed_) return *packed_;
     auto p = std::make_unique<Packed>();
     const size_t S = spheres.size(), T = triangles.size(), P = S + T;
-    const size_t Sp = align_up(S, RT_SPHERE_GROUP);
+    const size_t Sp = align_up(S, S >= RT_FILTER_FROM ? RT_FILTER_GROUP : RT_SPHERE_GROUP);
     p->n_sph     = (uint32_t)S;
     p->n_sph_pad = (uint32_t)Sp;
     const size_t Tp = align_up(T, RT_TRI_GROUP);

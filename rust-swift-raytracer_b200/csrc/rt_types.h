@@ -47,6 +47,10 @@ struct RtCameraData {
 struct RtFloat4 { float x, y, z, w; };
 
 #define RT_SPHERE_GROUP 8u
+#ifndef RT_FILTER_GROUP
+#define RT_FILTER_GROUP 8u     /* spheres per group of the FILTER kernels (a multiple of RT_SPHERE_GROUP) */
+#endif
+#define RT_FILTER_FROM  64u    /* sphere lists of at least this many run the FILTER kernels */
 #define RT_TRI_GROUP    2u
 
 // Everything the shading step needs about the primitive that was hit: one 32-byte record,
