@@ -14,6 +14,7 @@ module computes pixels.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -104,20 +105,42 @@ class ShardedRenderer:
         self.host_frame = (torch.empty((height, width), dtype=torch.int32).pin_memory() if rank == 0 else None)
         self.frame_ptr = 0        # peer mode: rank 0's frame (own allocation on rank 0, IPC mapping elsewhere)
         self._owns_frame = False
+        self.peer_error = None
         if self.gather == "peer" and world > 1:
+            # Map rank 0's frame into every rank.  CUDA IPC can be unavailable (containers without a
+            # shared IPC namespace, no peer access): all ranks then agree to use the NCCL gather — a
+            # slower data path with the same result, never a different computation.
             nbytes = width * height * 4
-            box = [None]
-            if rank == 0:
-                self.frame_ptr = rt.device_alloc(nbytes)
-                self._owns_frame = True
-                box[0] = rt.ipc_export(self.frame_ptr)
+            box, ok = [None], 1
+            try:
+                if rank == 0:
+                    self.frame_ptr = rt.device_alloc(nbytes)
+                    self._owns_frame = True
+                    box[0] = rt.ipc_export(self.frame_ptr)
+            except rt.RenderError as e:
+                ok, self.peer_error = 0, str(e)
             dist.broadcast_object_list(box, src=0)
             if rank != 0:
-                self.frame_ptr = rt.ipc_open(box[0])
-            self.token = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self.local = None
-            self.staging = None
-        else:
+                try:
+                    if box[0] is None:
+                        raise rt.RenderError("rank 0 could not export its frame")
+                    if os.environ.get("RT_DISABLE_IPC"):      # test hook for the fallback below
+                        raise rt.RenderError("CUDA IPC disabled by RT_DISABLE_IPC")
+                    self.frame_ptr = rt.ipc_open(box[0])
+                except rt.RenderError as e:
+                    ok, self.peer_error = 0, str(e)
+            self.token = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(self.token, op=dist.ReduceOp.MIN)
+            if int(self.token.item()) == 0:
+                if self.frame_ptr:
+                    (rt.device_free if self._owns_frame else rt.ipc_close)(self.frame_ptr)
+                self.frame_ptr, self._owns_frame = 0, False
+                self.gather = "nccl"
+            else:
+                self.token.zero_()
+                self.local = None
+                self.staging = None
+        if not (self.gather == "peer" and world > 1):
             self.gather = "nccl"
             self.local = alloc_compact(width, height, tile_rows, world, self.device)
             j = padded_tiles_per_rank(height, tile_rows, world)

@@ -492,6 +492,10 @@ def _dist_worker(rank, world, port, gather, q):
     import importlib
     import os
     import sys
+    expect = gather
+    if gather == "peer-unavailable":            # CUDA IPC fails on the non-zero ranks: everybody falls back
+        os.environ["RT_DISABLE_IPC"] = "1"
+        gather, expect = "peer", "nccl"
     import torch
     import torch.distributed as dist
     sys.path.insert(0, str(ROOT))
@@ -505,6 +509,7 @@ def _dist_worker(rank, world, port, gather, q):
     h = rt.load_world(scenes.example_world())
     W, H = 333, 170                                  # ragged: last tile is partial, tiles % world != 0
     r = multi.ShardedRenderer(rt, h, W, H, rank, world, tile_rows=16, gather=gather)
+    assert r.gather == expect, (r.gather, expect, r.peer_error)
     frame, rays = r.render(8, 8, passes=2, to_host=True, count_rays=True)
     frame2, _ = r.render(8, 8, passes=1, to_host=True)          # single pass == two progressive passes
     t = torch.tensor([rays], dtype=torch.int64, device="cuda")
@@ -516,7 +521,7 @@ def _dist_worker(rank, world, port, gather, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("gather", ["peer", "nccl"])
+@pytest.mark.parametrize("gather", ["peer", "nccl", "peer-unavailable"])
 def test_one_process_per_gpu_sharded_frame_equals_single_gpu(gpu_rt, scenes, gather):
     """The bench's N > 1 path (one process per GPU, torch.distributed/NCCL): tile shards +
     gather (peer stores through CUDA IPC, or dist.gather) == the single-GPU frame, bit for bit."""
