@@ -115,6 +115,31 @@ def test_render_abi_call_is_16spp_depth8(gpu_rt, ob, scenes):
     assert (fb.pixels[:, :, 3] == 255).all()            # alpha is always 255 (color.rs:21-23)
 
 
+def test_plain_c_caller_of_the_reference_abi(gpu_rt, ob, scenes, tmp_path):
+    """tests/c_caller/c_caller.c uses nothing but raytracer.h (load_world / move_camera_position /
+    render) — the counterpart of examples/c_raytracer.rs: compiled with gcc against include/,
+    linked with libraytracer.so, its frame equals the oracle's."""
+    import subprocess
+    lib = ROOT / "rust-swift-raytracer_b200" / "lib"
+    exe = tmp_path / "c_caller"
+    r = subprocess.run(["/usr/bin/gcc", "-std=c11", "-O1", "-Wall", "-Werror", f"-I{ROOT / 'include'}",
+                        str(ROOT / "tests" / "c_caller" / "c_caller.c"), f"-L{lib}", "-lraytracer",
+                        f"-Wl,-rpath,{lib}", "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    world_txt = tmp_path / "world.txt"
+    world_txt.write_text(scenes.example_world())
+    cam, world = ob.parse_input(scenes.example_world())
+    for move in (None, (0.25, 0.125, -0.5)):
+        out = tmp_path / "frame.rgba"
+        args = [str(exe), str(world_txt), "200", "200", str(out)] + ([str(v) for v in move] if move else [])
+        r = subprocess.run(args, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (r.returncode, r.stderr)
+        got = np.frombuffer(out.read_bytes(), dtype=np.uint8).reshape(200, 200, 4)
+        c = ob.move_camera_position(cam, *move) if move else cam
+        want, _, _ = ob.ray_trace(world, c, 200, 200, 16, 8)
+        assert np.array_equal(got, want)
+
+
 def test_camera_move_then_render(gpu_rt, ob, scenes):
     """GameView.swift:198-216: handle->camera = move_camera_position(handle->camera, ...)."""
     rt = gpu_rt
