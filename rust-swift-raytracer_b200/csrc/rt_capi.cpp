@@ -163,6 +163,9 @@ Rust_CFramebuffer render_with_options(Rust_CFramebuffer fb, const Rust_WorldHand
         if (n_dev > 1 && o.shard_count <= 1)
             rt::ray_trace_multi(*handle->world->world, handle->camera->camera, fb.width, fb.height, o,
                                 reinterpret_cast<rt::ColorU8*>(fb.pixels), n_dev);
+        else if (rt::is_device_memory(fb.pixels))      // a caller that keeps its frame on the GPU (e.g. for display)
+            rt::ray_trace_into(*handle->world->world, handle->camera->camera, fb.width, fb.height, o, nullptr,
+                               fb.pixels, nullptr, nullptr);
         else
             rt::ray_trace_into(*handle->world->world, handle->camera->camera, fb.width, fb.height, o,
                                reinterpret_cast<rt::ColorU8*>(fb.pixels), nullptr, nullptr, nullptr);

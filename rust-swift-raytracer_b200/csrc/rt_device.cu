@@ -679,6 +679,14 @@ void copy_to_host(void* host_dst, const void* device_src, size_t bytes, void* st
     RT_CUDA(cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
 }
 
+bool is_device_memory(const void* p)
+{
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice;
+}
+
 void* alloc_pinned(size_t bytes)
 {
     void* p = nullptr;

@@ -206,6 +206,7 @@ void* ipc_open(const unsigned char handle[64]);
 void  ipc_close(void* p);
 void  copy_to_host(void* host_dst, const void* device_src, size_t bytes, void* stream);
 // Pinned host allocations for callers that want the frame DMA'd straight into their buffer.
+bool  is_device_memory(const void* p);   // true for cudaMalloc'ed memory (a frame that should stay on the GPU)
 void* alloc_pinned(size_t bytes);
 void  free_pinned(void* p);
 

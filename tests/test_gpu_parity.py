@@ -307,6 +307,20 @@ def test_device_resident_render_on_a_torch_stream(gpu_rt, ob, scenes):
     assert np.array_equal(out.cpu().numpy().view(np.uint8).reshape(H, W, 4), want)
 
 
+def test_render_into_a_device_resident_framebuffer(gpu_rt, scenes):
+    """render() with framebuffer.pixels pointing at device memory leaves the frame on the GPU."""
+    import torch
+    rt = gpu_rt
+    W, H = 96, 54
+    h = rt.load_world(scenes.default_world())
+    want, _ = _render(rt, h, W, H, 16, 8)
+    out = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+    rt.lib().render(rt._CFramebuffer(W, H, out.data_ptr()), h.ptr)
+    assert rt.last_error() == ""
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint8).reshape(H, W, 4), want)
+
+
 def test_pinned_and_pageable_destinations_agree(gpu_rt, scenes):
     rt = gpu_rt
     h = rt.load_world(scenes.default_world())
