@@ -53,6 +53,15 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of one render-kernel launch, from the committed
 # `ncu --set full` captures (profiles/r01_bench.md); None where no capture of that exact launch exists.
 NCU_TRAFFIC_BYTES = {("c2", False): 36352}      # 36 KB read, 0 B written: the 8.3 MB frame stays in the 126 MB L2
+# Counters of the same captures, quoted (not measured in this run) so that the line explains its own
+# `frac`: on the 8-sphere scene the counted-flops model covers less than half of the instructions a
+# segment needs (IEEE divide/sqrt sequences, integer RNG, predicates), and the kernel is issue-bound.
+NCU_CONTEXT = {
+    ("c2", False): {"issue_slots_busy": 0.897, "ipc": 3.59, "fp32_pipe_active": 0.443, "active_lanes_per_warp": 22.4,
+                    "source": "profiles/r01_c2_exact_v3_full_size_light.txt, r01_c2_exact_v4_spp16_details.txt"},
+    ("c3", False): {"issue_slots_busy": 0.728, "ipc": 2.91, "fp32_pipe_active": 0.500, "active_lanes_per_warp": 30.4,
+                    "source": "profiles/r01_c3_exact_v4_spp8_details.txt (64-register build)"},
+}
 
 
 def scene_text(scenes, key):
@@ -384,7 +393,8 @@ def main():
                                     "(MEASURED_PEAKS.json has no FP32 CUDA-core figure; nominal 2*128*148*1.965 GHz = 74.4)",
                      "flops_per_step": flops,
                      "flops_model": "rays*(17*S + 12*T + 60) + samples*34 + pixels*11, FMA = 2 (SURVEY.md 8d)",
-                     "hbm_bytes_per_step": W * H * 4 + (passes - 1) * 2 * W * H * 16},
+                     "hbm_bytes_per_step": W * H * 4 + (passes - 1) * 2 * W * H * 16,
+                     "ncu_context": NCU_CONTEXT.get((args.workload, fast)) if n_gpus == 1 else None},
         "clocks": clocks.summary(),
     }
     if one_process:
