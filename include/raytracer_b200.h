@@ -24,6 +24,10 @@ extern "C" {
 #define RT_OPT_PIXEL_ITEMS  0x40u /* scheduling only: a lane always owns a whole pixel */
 #define RT_OPT_SAMPLE_ITEMS 0x80u /* scheduling only: work items are single samples, summed in order by a
                                      second kernel (default: chosen from the scene and frame size) */
+#define RT_OPT_GROUP_CULL   0x100u /* acceleration, opt-in and reported separately: spheres are kept in
+                                      spatial groups of 8 with conservative bounding spheres; a ray tests only the
+                                      groups it can touch.  Same pixels and ray counts, fewer sphere tests.
+                                      Worlds with fewer than 64 spheres ignore it. */
 #define RT_OPT_FULL_FRAME_OUT 0x20u /* rt_render_device with shard_count > 1: device_pixels / device_accum are
                                        FULL width*height frames (e.g. another GPU's frame mapped through CUDA IPC
                                        or peer access); this shard's tiles are stored at their frame offsets */
@@ -48,7 +52,7 @@ typedef struct RtRenderStats {
   uint32_t peer_gather; /* 1: shards stored their tiles straight into device 0's frame (NVLink peer stores) */
   uint32_t filtered;    /* 1: the exact kernel put its conservative FMA filter in front of the sphere tests */
   uint32_t sample_items;/* 1: work items were single samples; a second kernel summed them in order */
-  uint32_t reserved;
+  uint32_t culled;      /* 1: the CULL kernels ran (RT_OPT_GROUP_CULL) */
 } RtRenderStats;
 
 /* common.rs:289-294 `Options`, extended.  Zero-initialise, then set struct_size. */

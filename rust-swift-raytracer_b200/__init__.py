@@ -39,6 +39,7 @@ OPT_NO_RESOLVE = 0x10
 OPT_FULL_FRAME_OUT = 0x20
 OPT_PIXEL_ITEMS = 0x40
 OPT_SAMPLE_ITEMS = 0x80
+OPT_GROUP_CULL = 0x100
 DIFFUSE, METAL, DIELECTRIC, EMISSION = 0, 1, 2, 3   # materials.rs:7-12
 
 
@@ -67,7 +68,7 @@ class RenderStats(C.Structure):
                 ("total_ms", C.c_float), ("launches", C.c_uint32), ("grid", C.c_uint32),
                 ("smem_bytes", C.c_uint32), ("resident", C.c_uint32), ("block", C.c_uint32),
                 ("devices", C.c_uint32), ("peer_gather", C.c_uint32), ("filtered", C.c_uint32),
-                ("sample_items", C.c_uint32), ("reserved", C.c_uint32)]
+                ("sample_items", C.c_uint32), ("culled", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -223,11 +224,12 @@ class Options:
     full_frame_out: bool = False         # sharded, but the device buffers are full frames (peer / IPC mapped)
     n_devices: int = 0                   # > 1: this process renders on devices 0..n-1 (render_with_options only)
     sample_items: Optional[bool] = None  # scheduling: None auto, False whole pixels per lane, True single samples
+    group_cull: bool = False             # opt-in acceleration: bounding spheres over groups of 8 spheres (same hits)
 
     def _c(self, stats: Optional[RenderStats]) -> _RenderOptions:
         flags = ((OPT_FIXED_JITTER if self.fixed_jitter else 0) | (OPT_FAST_MATH if self.fast_math else 0) |
                  (OPT_ACCUM_IN if self.accum_in else 0) | (OPT_ACCUM_OUT if self.accum_out else 0) |
-                 (OPT_NO_RESOLVE if self.no_resolve else 0) | (OPT_FULL_FRAME_OUT if self.full_frame_out else 0) |
+                 (OPT_NO_RESOLVE if self.no_resolve else 0) | (OPT_FULL_FRAME_OUT if self.full_frame_out else 0) | (OPT_GROUP_CULL if self.group_cull else 0) |
                  (0 if self.sample_items is None else OPT_SAMPLE_ITEMS if self.sample_items else OPT_PIXEL_ITEMS))
         o = _RenderOptions(C.sizeof(_RenderOptions), int(self.samples_per_pixel), int(self.max_ray_bounces),
                            int(self.seed) & 0xFFFFFFFF, flags, int(self.sample_begin), int(self.resolve_spp),

@@ -62,6 +62,7 @@ rt::Options to_options(const RtRenderOptions* o)
     r.accum_out         = (c.flags & RT_OPT_ACCUM_OUT) != 0;
     r.no_resolve        = (c.flags & RT_OPT_NO_RESOLVE) != 0;
     r.full_frame_out    = (c.flags & RT_OPT_FULL_FRAME_OUT) != 0;
+    r.group_cull        = (c.flags & RT_OPT_GROUP_CULL) != 0;
     r.n_devices         = (int32_t)c.n_devices;
     r.sample_items      = (c.flags & RT_OPT_SAMPLE_ITEMS) ? 1 : (c.flags & RT_OPT_PIXEL_ITEMS) ? 0 : -1;
     r.sample_begin      = c.sample_begin;
@@ -78,7 +79,7 @@ void export_stats(const rt::RenderStats& s, RtRenderStats* out)
     out->rays = s.rays; out->samples = s.samples; out->kernel_ms = s.kernel_ms; out->total_ms = s.total_ms;
     out->launches = s.launches; out->grid = s.grid; out->smem_bytes = s.smem_bytes; out->resident = s.resident;
     out->block = s.block; out->devices = s.devices; out->peer_gather = s.peer_gather; out->filtered = s.filtered;
-    out->sample_items = s.sample_items; out->reserved = 0;
+    out->sample_items = s.sample_items; out->culled = s.culled;
 }
 
 template <class F>

@@ -24,10 +24,10 @@ namespace rt {
 // defined in rt_kernels_exact.cu / rt_kernels_fast.cu
 cudaError_t launch_render_exact(const RtFrameParams&, const RtSceneView&, int grid, size_t smem_limit, cudaStream_t);
 cudaError_t launch_render_fast(const RtFrameParams&, const RtSceneView&, int grid, size_t smem_limit, cudaStream_t);
-cudaError_t occupancy_exact(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
-                            size_t* hot_bytes, int* resident, int* filtered);
-cudaError_t occupancy_fast(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
-                           size_t* hot_bytes, int* resident, int* filtered);
+cudaError_t occupancy_exact(const RtSceneView& G, size_t smem_limit, bool cull, int* blocks_per_sm, int* block_size,
+                            size_t* hot_bytes, int* resident, int* sph_mode);
+cudaError_t occupancy_fast(const RtSceneView& G, size_t smem_limit, bool cull, int* blocks_per_sm, int* block_size,
+                           size_t* hot_bytes, int* resident, int* sph_mode);
 cudaError_t launch_resolve_samples_exact(const RtFrameParams&, cudaStream_t);
 cudaError_t launch_resolve_samples_fast(const RtFrameParams&, cudaStream_t);
 cudaError_t launch_selftest_division(unsigned long long n_per_thread, uint32_t seed, int grid, int block,
@@ -65,8 +65,8 @@ struct DeviceContext {
     unsigned char* h_stage = nullptr;  size_t h_stage_cap = 0;   // pinned staging for pageable destinations
     RtFloat4*    d_samples = nullptr;  size_t d_samples_cap = 0; // per-sample colours of the sample-item mode
     RtFloat4*    d_accum = nullptr;    size_t d_accum_cap = 0;   // hand-over sums between sample-item chunks
-    struct Geometry { int per_sm = 0, block = 0, resident = 0, filtered = 0; size_t hot_bytes = 0; };
-    std::map<std::tuple<uint32_t, uint32_t, int>, Geometry> occupancy;   // (Sp, Tp, fast) -> launch geometry
+    struct Geometry { int per_sm = 0, block = 0, resident = 0, sph_mode = 0; size_t hot_bytes = 0; };
+    std::map<std::tuple<uint32_t, uint32_t, int, int>, Geometry> occupancy;   // (Sp, Tp, fast, cull) -> launch geometry
 };
 
 std::mutex                    g_mutex;          // one render at a time per process (lib.rs is single-threaded)
@@ -185,7 +185,7 @@ struct ShardLaunch {
     size_t       out_pixels = 0;
     int          grid = 0, block = 0;
     size_t       hot_bytes = 0, smem_limit = 0;
-    bool         resident = false, filtered = false, sample_items = false;
+    bool         resident = false, filtered = false, culled = false, sample_items = false;
     uint32_t     launches = 0;
     CounterSlot* slot = nullptr;
     uint32_t*    d_out = nullptr;
@@ -235,7 +235,7 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     P.seed         = opt.seed;
     P.flags        = (opt.fixed_jitter ? RT_FLAG_FIXED_JITTER : 0u) | (opt.accum_in ? RT_FLAG_ACCUM_IN : 0u) |
               (opt.accum_out ? RT_FLAG_ACCUM_OUT : 0u) | (opt.no_resolve ? RT_FLAG_NO_RESOLVE : 0u) |
-              (L.compact ? RT_FLAG_COMPACT_OUT : 0u);
+              (L.compact ? RT_FLAG_COMPACT_OUT : 0u) | (opt.group_cull ? RT_FLAG_GROUP_CULL : 0u);
     P.tile_rows    = opt.tile_rows;
     P.tile_first   = opt.shard_index;
     P.tile_stride  = opt.shard_count;
@@ -295,17 +295,18 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
 
     // launch geometry: persistent CTAs, resident-CTA count from the occupancy API
     L.smem_limit = ctx.smem_optin > 1024 ? ctx.smem_optin - 1024 : 0;   // static smem: the mbarrier
-    auto& occ    = ctx.occupancy[{scene.view.n_sph_pad, scene.view.n_tri_pad, opt.fast_math ? 1 : 0}];
+    auto& occ    = ctx.occupancy[{scene.view.n_sph_pad, scene.view.n_tri_pad, opt.fast_math ? 1 : 0, opt.group_cull ? 1 : 0}];
     if (occ.per_sm == 0) {
-        RT_CUDA(opt.fast_math ? occupancy_fast(scene.view, L.smem_limit, &occ.per_sm, &occ.block, &occ.hot_bytes,
-                                               &occ.resident, &occ.filtered)
-                              : occupancy_exact(scene.view, L.smem_limit, &occ.per_sm, &occ.block, &occ.hot_bytes,
-                                                &occ.resident, &occ.filtered));
+        RT_CUDA(opt.fast_math ? occupancy_fast(scene.view, L.smem_limit, opt.group_cull, &occ.per_sm, &occ.block,
+                                               &occ.hot_bytes, &occ.resident, &occ.sph_mode)
+                              : occupancy_exact(scene.view, L.smem_limit, opt.group_cull, &occ.per_sm, &occ.block,
+                                                &occ.hot_bytes, &occ.resident, &occ.sph_mode));
         if (occ.per_sm < 1) throw std::runtime_error("render kernel does not fit on this device");
     }
     L.hot_bytes = occ.hot_bytes;
     L.resident  = occ.resident != 0;
-    L.filtered  = occ.filtered != 0;
+    L.filtered  = occ.sph_mode != RT_SPH_DIRECT;
+    L.culled    = occ.sph_mode == RT_SPH_CULL;
     L.block = occ.block;
     const uint64_t work_slots = L.sample_items ? slots * (uint64_t)chunk_spp : slots;
     const uint64_t want_ctas = (work_slots + (uint64_t)L.block - 1) / (uint64_t)L.block;
@@ -437,6 +438,7 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
         st.resident   = L.resident ? 1u : 0u;
         st.smem_bytes = st.resident ? (uint32_t)L.hot_bytes : 0u;
         st.filtered   = L.filtered ? 1u : 0u;
+        st.culled     = L.culled ? 1u : 0u;
         if (n_tiles > 0) {
             RT_CUDA(cudaMemcpyAsync(ctx.h_slot, L.slot, sizeof(CounterSlot), cudaMemcpyDeviceToHost, stream));
             RT_CUDA(cudaStreamSynchronize(stream));
@@ -559,6 +561,7 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
         st.resident   = launches[0].resident ? 1u : 0u;
         st.smem_bytes = st.resident ? (uint32_t)launches[0].hot_bytes : 0u;
         st.filtered   = launches[0].filtered ? 1u : 0u;
+        st.culled     = launches[0].culled ? 1u : 0u;
         st.devices    = (uint32_t)N;
         st.peer_gather = peer ? 1u : 0u;
         for (int d = 0; d < N; ++d) {

@@ -92,7 +92,7 @@ struct RenderStats {
     uint32_t peer_gather = 0;    // 1: shards stored their tiles straight into device 0's frame (NVLink peer stores)
     uint32_t filtered   = 0;     // 1: exact kernel ran its conservative sphere filter (large sphere lists)
     uint32_t sample_items = 0;   // 1: work items were single samples (ordered sum by the resolve kernel)
-    uint32_t reserved   = 0;
+    uint32_t culled     = 0;     // 1: the CULL kernels ran (group bounds in front of the filter)
 };
 
 // common.rs:289-294, extended.  The reference fields keep their names.
@@ -117,6 +117,8 @@ struct Options {
                                             // peer-mapped frame on another GPU): tiles land at their frame offset
     int32_t  n_devices      = 0;            // > 1: one process drives devices 0..n-1 (ray_trace_multi)
     int32_t  sample_items   = -1;           // work-item granularity: -1 auto, 0 whole pixels, 1 single samples
+    bool     group_cull     = false;        // opt-in: skip whole groups of spheres through bounding spheres (same
+                                            // hits; a separately reported mode — it changes the work done)
     RenderStats* stats      = nullptr;
 };
 
@@ -136,8 +138,8 @@ struct World {
     struct Packed {
         std::vector<unsigned char> blob;
         size_t off_sph = 0, off_tri_plane = 0, off_sph_filter = 0, off_sph_r2 = 0, off_tri_cull = 0, off_tri_v = 0,
-               off_info = 0;
-        uint32_t n_sph = 0, n_sph_pad = 0, n_tri = 0, n_tri_pad = 0;
+               off_info = 0, off_cull_bound = 0, off_cull_sph = 0, off_cull_r2 = 0, off_cull_orig = 0;
+        uint32_t n_sph = 0, n_sph_pad = 0, n_tri = 0, n_tri_pad = 0, n_groups = 0;
         RtSceneView view(const unsigned char* base) const;
     };
     const Packed& packed() const;

@@ -32,10 +32,11 @@
 namespace rt {
 
 // bytes of the hot lists a CTA stages (block A or block B of rt_types.h)
-__host__ __device__ inline uint32_t rt_hot_bytes(const RtSceneView& G, bool filter)
+__host__ __device__ inline uint32_t rt_hot_bytes(const RtSceneView& G, int sph_mode)
 {
+    if (sph_mode == RT_SPH_CULL) return (10u * G.n_groups + G.n_tri_pad) * (uint32_t)sizeof(RtFloat4);
     uint32_t b = (G.n_sph_pad + G.n_tri_pad) * (uint32_t)sizeof(RtFloat4);
-    if (filter) b += ((G.n_sph_pad * (uint32_t)sizeof(float)) + 15u) & ~15u;
+    if (sph_mode == RT_SPH_FILTER) b += ((G.n_sph_pad * (uint32_t)sizeof(float)) + 15u) & ~15u;
     return b;
 }
 
@@ -133,28 +134,38 @@ __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_
 #define RT_MIN_CTAS_FILTER 3  // FILTER kernels: 80 registers measured faster than 64 (the loop is FFMA-bound,
 #endif                        // not latency-bound: C3 fast 399 -> 369 ms, exact 439 -> 431 ms)
 
-template <bool FAST, bool SMEM, int BLOCK, bool FILTER, bool TRIS>
-__global__ void __launch_bounds__(BLOCK, BLOCK != 256 ? 1 : FILTER ? RT_MIN_CTAS_FILTER : RT_MIN_CTAS_SMALL) rt_render_kernel(const __grid_constant__ RtFrameParams P,
+template <bool FAST, bool SMEM, int BLOCK, int SPH, bool TRIS>
+__global__ void __launch_bounds__(BLOCK, BLOCK != 256 ? 1 : SPH != RT_SPH_DIRECT ? RT_MIN_CTAS_FILTER : RT_MIN_CTAS_SMALL) rt_render_kernel(const __grid_constant__ RtFrameParams P,
                                                          const __grid_constant__ RtSceneView  G)
 {
     extern __shared__ __align__(128) unsigned char rt_smem[];
     __shared__ __align__(8) unsigned long long rt_mbar;
 
-    // the hot lists: block A {sph | tri_plane}, or block B {sph_filter | tri_plane | sph_r2} (rt_types.h),
-    // each one contiguous range of the scene blob
+    // the hot lists — block A {sph | tri_plane}, block B {sph_filter | tri_plane | sph_r2} or block C
+    // {cull_bound | cull_sph | tri_plane} of rt_types.h — each one contiguous range of the scene blob
     const RtFloat4* sph;
     const RtFloat4* tri_plane;
     const float*    sph_r2 = nullptr;
+    CullView        cv{G.cull_bound, G.cull_sph, G.cull_r2, G.cull_orig, G.n_groups};
     if (SMEM) {
-        const uint32_t hot_bytes = rt_hot_bytes(G, FILTER);
-        if (hot_bytes) stage_scene_tma(rt_smem, FILTER ? G.sph_filter : G.sph, hot_bytes, &rt_mbar);
-        sph       = reinterpret_cast<const RtFloat4*>(rt_smem);
-        tri_plane = sph + G.n_sph_pad;
-        if (FILTER) sph_r2 = reinterpret_cast<const float*>(tri_plane + G.n_tri_pad);
+        const uint32_t hot_bytes = rt_hot_bytes(G, SPH);
+        const void*    src       = SPH == RT_SPH_CULL ? (const void*)G.cull_bound
+                                 : SPH == RT_SPH_FILTER ? (const void*)G.sph_filter : (const void*)G.sph;
+        if (hot_bytes) stage_scene_tma(rt_smem, src, hot_bytes, &rt_mbar);
+        if (SPH == RT_SPH_CULL) {
+            cv.bound  = reinterpret_cast<const RtFloat4*>(rt_smem);
+            cv.sph9   = cv.bound + G.n_groups;
+            sph       = cv.sph9;                               // not walked in list order in this mode
+            tri_plane = cv.sph9 + 9u * G.n_groups;
+        } else {
+            sph       = reinterpret_cast<const RtFloat4*>(rt_smem);
+            tri_plane = sph + G.n_sph_pad;
+            if (SPH == RT_SPH_FILTER) sph_r2 = reinterpret_cast<const float*>(tri_plane + G.n_tri_pad);
+        }
     } else {
-        sph       = FILTER ? G.sph_filter : G.sph;
+        sph       = SPH == RT_SPH_FILTER ? G.sph_filter : G.sph;
         tri_plane = G.tri_plane;
-        if (FILTER) sph_r2 = G.sph_r2;
+        if (SPH == RT_SPH_FILTER) sph_r2 = G.sph_r2;
     }
 
     const uint32_t FULL = 0xffffffffu;
@@ -216,7 +227,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK != 256 ? 1 : FILTER ? RT_MIN_CTAS
         // ---- 2. one ray segment per live lane (sample start, World::hit, scatter, accumulate) ----
         bool sample_done = false;
         if (L.have && trace) {
-            sample_done = trace_segment<FAST, FILTER, TRIS>(L, P, G, sph, sph_r2, tri_plane);
+            sample_done = trace_segment<FAST, SPH, TRIS>(L, P, G, sph, sph_r2, cv, tri_plane);
             ++segments;
         }
 
@@ -302,29 +313,34 @@ constexpr int      kBlockLarge    = RT_BLOCK_LARGE;
 constexpr size_t   kLargeSmemFrom = 56 * 1024;   // above this, < 4 CTAs of 256 threads would fit
 constexpr uint32_t kFilterFrom    = RT_FILTER_FROM;   // spheres from which the kernels filter first
 
-struct RenderVariant { bool smem; int block; bool filter; bool tris; size_t hot_bytes; };
+struct RenderVariant { bool smem; int block; int sph; bool tris; size_t hot_bytes; };
 
 template <bool FAST>
-inline RenderVariant choose_variant(const RtSceneView& G, size_t smem_limit)
+inline RenderVariant choose_variant(const RtSceneView& G, size_t smem_limit, bool cull)
 {
     RenderVariant v;
-    v.filter    = G.n_sph_pad >= kFilterFrom;
+    v.sph       = (cull && G.n_groups > 0) ? RT_SPH_CULL : G.n_sph_pad >= kFilterFrom ? RT_SPH_FILTER : RT_SPH_DIRECT;
     v.tris      = G.n_tri_pad > 0;
-    v.hot_bytes = rt_hot_bytes(G, v.filter);
+    v.hot_bytes = rt_hot_bytes(G, v.sph);
     v.smem      = v.hot_bytes <= smem_limit;
     v.block     = (v.smem && v.hot_bytes > kLargeSmemFrom) ? kBlockLarge : kBlockSmall;
     return v;
 }
 
-// f(kernel pointer, block) for the variant's instantiation.  Large sphere lists get the
-// FILTER kernels; worlds without triangles get kernels without the triangle code.
+// f(kernel pointer, block) for the variant's instantiation.  Large sphere lists get the FILTER
+// (or, on request, CULL) kernels; worlds without triangles get kernels without the triangle code.
+template <bool FAST, bool SMEM, int BLOCK, int SPH, class F>
+cudaError_t with_kernel4(const RenderVariant& v, F&& f)
+{
+    return v.tris ? f(rt_render_kernel<FAST, SMEM, BLOCK, SPH, true>, BLOCK)
+                  : f(rt_render_kernel<FAST, SMEM, BLOCK, SPH, false>, BLOCK);
+}
 template <bool FAST, bool SMEM, int BLOCK, class F>
 cudaError_t with_kernel3(const RenderVariant& v, F&& f)
 {
-    if (v.filter) return v.tris ? f(rt_render_kernel<FAST, SMEM, BLOCK, true, true>, BLOCK)
-                                : f(rt_render_kernel<FAST, SMEM, BLOCK, true, false>, BLOCK);
-    return v.tris ? f(rt_render_kernel<FAST, SMEM, BLOCK, false, true>, BLOCK)
-                  : f(rt_render_kernel<FAST, SMEM, BLOCK, false, false>, BLOCK);
+    if (v.sph == RT_SPH_CULL) return with_kernel4<FAST, SMEM, BLOCK, RT_SPH_CULL>(v, f);
+    if (v.sph == RT_SPH_FILTER) return with_kernel4<FAST, SMEM, BLOCK, RT_SPH_FILTER>(v, f);
+    return with_kernel4<FAST, SMEM, BLOCK, RT_SPH_DIRECT>(v, f);
 }
 template <bool FAST, class F>
 cudaError_t with_kernel(const RenderVariant& v, F&& f)
@@ -339,7 +355,7 @@ template <bool FAST>
 cudaError_t launch_render(const RtFrameParams& P, const RtSceneView& G, int grid, size_t smem_limit,
                           cudaStream_t stream)
 {
-    const RenderVariant v = choose_variant<FAST>(G, smem_limit);
+    const RenderVariant v = choose_variant<FAST>(G, smem_limit, (P.flags & RT_FLAG_GROUP_CULL) != 0);
     return with_kernel<FAST>(v, [&](auto k, int block) -> cudaError_t {
         if (v.smem) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
@@ -352,11 +368,11 @@ cudaError_t launch_render(const RtFrameParams& P, const RtSceneView& G, int grid
 
 // Resident CTAs per SM, the CTA width and the staged bytes launch_render will use for this scene.
 template <bool FAST>
-cudaError_t render_occupancy(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
-                             size_t* hot_bytes, int* resident, int* filtered)
+cudaError_t render_occupancy(const RtSceneView& G, size_t smem_limit, bool cull, int* blocks_per_sm, int* block_size,
+                             size_t* hot_bytes, int* resident, int* sph_mode)
 {
-    const RenderVariant v = choose_variant<FAST>(G, smem_limit);
-    *block_size = v.block; *hot_bytes = v.hot_bytes; *resident = v.smem ? 1 : 0; *filtered = v.filter ? 1 : 0;
+    const RenderVariant v = choose_variant<FAST>(G, smem_limit, cull);
+    *block_size = v.block; *hot_bytes = v.hot_bytes; *resident = v.smem ? 1 : 0; *sph_mode = v.sph;
     return with_kernel<FAST>(v, [&](auto k, int block) -> cudaError_t {
         if (v.smem) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);

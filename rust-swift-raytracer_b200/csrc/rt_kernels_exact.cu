@@ -18,10 +18,10 @@ cudaError_t launch_resolve_samples_exact(const RtFrameParams& P, cudaStream_t st
     return launch_resolve_samples<false>(P, stream);
 }
 
-cudaError_t occupancy_exact(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
-                            size_t* hot_bytes, int* resident, int* filtered)
+cudaError_t occupancy_exact(const RtSceneView& G, size_t smem_limit, bool cull, int* blocks_per_sm, int* block_size,
+                            size_t* hot_bytes, int* resident, int* sph_mode)
 {
-    return render_occupancy<false>(G, smem_limit, blocks_per_sm, block_size, hot_bytes, resident, filtered);
+    return render_occupancy<false>(G, smem_limit, cull, blocks_per_sm, block_size, hot_bytes, resident, sph_mode);
 }
 
 // ---- self-test of the shared-reciprocal divide (rt_trace.cuh, div3 / pixel_uv) -----------

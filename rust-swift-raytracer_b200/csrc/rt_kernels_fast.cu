@@ -17,10 +17,10 @@ cudaError_t launch_resolve_samples_fast(const RtFrameParams& P, cudaStream_t str
     return launch_resolve_samples<true>(P, stream);
 }
 
-cudaError_t occupancy_fast(const RtSceneView& G, size_t smem_limit, int* blocks_per_sm, int* block_size,
-                            size_t* hot_bytes, int* resident, int* filtered)
+cudaError_t occupancy_fast(const RtSceneView& G, size_t smem_limit, bool cull, int* blocks_per_sm, int* block_size,
+                            size_t* hot_bytes, int* resident, int* sph_mode)
 {
-    return render_occupancy<true>(G, smem_limit, blocks_per_sm, block_size, hot_bytes, resident, filtered);
+    return render_occupancy<true>(G, smem_limit, cull, blocks_per_sm, block_size, hot_bytes, resident, sph_mode);
 }
 
 // ---- FP32 peak microbenchmark: 16 independent FFMA chains per thread -------------------

@@ -7,6 +7,7 @@
 #include "rt_host.hpp"
 
 #include <clocale>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -131,6 +132,11 @@ RtSceneView World::Packed::view(const unsigned char* base) const
     v.tri_plane = reinterpret_cast<const RtFloat4*>(base + off_tri_plane);
     v.sph_filter = reinterpret_cast<const RtFloat4*>(base + off_sph_filter);
     v.sph_r2     = reinterpret_cast<const float*>(base + off_sph_r2);
+    v.cull_bound = reinterpret_cast<const RtFloat4*>(base + off_cull_bound);
+    v.cull_sph   = reinterpret_cast<const RtFloat4*>(base + off_cull_sph);
+    v.cull_r2    = reinterpret_cast<const float*>(base + off_cull_r2);
+    v.cull_orig  = reinterpret_cast<const uint32_t*>(base + off_cull_orig);
+    v.n_groups   = n_groups;
     v.tri_cull  = reinterpret_cast<const RtFloat4*>(base + off_tri_cull);
     v.tri_v     = reinterpret_cast<const RtFloat4*>(base + off_tri_v);
     v.info      = reinterpret_cast<const RtPrimInfo*>(base + off_info);
@@ -201,6 +207,111 @@ void triangle_cull_record(const Triangle& t, RtFloat4 out[3])
 }
 }   // namespace
 
+// ---- block C: spatial order and group bounds of the CULL kernels (rt_trace.cuh, cull_spheres) ----
+// Spheres much larger than the typical one (a ground sphere) would blow up the bound of any
+// group they sit in, so they come first, in groups of their own that always pass; the rest
+// are sorted along a Morton curve through their centres and cut into groups of 8.
+namespace {
+struct CullOrder { std::vector<std::vector<uint32_t>> groups; size_t always = 0; };   // groups[g] = list indices
+
+uint32_t morton3(uint32_t x, uint32_t y, uint32_t z)
+{
+    auto spread = [](uint32_t v) { v &= 0x3ffu; v = (v | (v << 16)) & 0x30000ffu; v = (v | (v << 8)) & 0x300f00fu;
+                                   v = (v | (v << 4)) & 0x30c30c3u; v = (v | (v << 2)) & 0x9249249u; return v; };
+    return spread(x) | (spread(y) << 1) | (spread(z) << 2);
+}
+
+CullOrder cull_order(const std::vector<Sphere>& sph)
+{
+    CullOrder o;
+    const size_t S = sph.size();
+    std::vector<float> radii(S);
+    for (size_t i = 0; i < S; ++i) radii[i] = std::fabs(sph[i].radius);
+    std::vector<float> sorted = radii;
+    std::nth_element(sorted.begin(), sorted.begin() + S / 2, sorted.end());
+    const float big = 8.0f * sorted[S / 2];
+    std::vector<uint32_t> large, small;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (size_t i = 0; i < S; ++i) {
+        const Sphere& s = sph[i];
+        const bool finite = std::isfinite(s.center.x) && std::isfinite(s.center.y) && std::isfinite(s.center.z) &&
+                            std::isfinite(s.radius);
+        if (!finite || !(radii[i] <= big)) { large.push_back((uint32_t)i); continue; }
+        small.push_back((uint32_t)i);
+        const double c[3] = {s.center.x, s.center.y, s.center.z};
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], c[a]); hi[a] = std::max(hi[a], c[a]); }
+    }
+    std::vector<std::pair<uint32_t, uint32_t>> keyed(small.size());
+    for (size_t k = 0; k < small.size(); ++k) {
+        const Sphere& s = sph[small[k]];
+        const double c[3] = {s.center.x, s.center.y, s.center.z};
+        uint32_t q[3];
+        for (int a = 0; a < 3; ++a) {
+            const double ext = hi[a] - lo[a];
+            q[a] = ext > 0 ? (uint32_t)std::min(1023.0, (c[a] - lo[a]) / ext * 1023.0) : 0u;
+        }
+        keyed[k] = {morton3(q[0], q[1], q[2]), small[k]};
+    }
+    std::sort(keyed.begin(), keyed.end());
+    for (size_t k = 0; k < large.size(); k += 8)
+        o.groups.emplace_back(large.begin() + k, large.begin() + std::min(k + 8, large.size()));
+    o.always = o.groups.size();
+    for (size_t k = 0; k < keyed.size(); k += 8) {
+        std::vector<uint32_t> g;
+        for (size_t j = k; j < std::min(k + 8, keyed.size()); ++j) g.push_back(keyed[j].second);
+        o.groups.push_back(std::move(g));
+    }
+    return o;
+}
+
+// Bound of a group (rt_trace.cuh cull_spheres gives the derivation): a member can pass its filter
+// only if the ray's line passes within  R(o) = A + B|o|  of the group centre cB, where
+//   A = Rgeo + B*Cg,  Rgeo = max_k(|c_k - cB| + r_k),  Cg = max_k(|c_k| + r_k),  B = RT_CULL_B.
+// The kernel evaluates  (o.d - cB.d)^2 - (o.o - 2 cB.o + cB.cB) + R(o)^2  + margins as
+//   fma(hb,hb,-t) + fma(gB, |o|, -kray),   t = -2 cB.o + wB,
+//   wB = cB.cB - A^2 - m (cB.cB + A^2)  (rounded down),   gB = 2AB (1 + m)  (rounded up).
+void build_cull_block(const CullOrder& order, const RtFloat4* sph_filter, const float* sph_r2, RtFloat4* bound,
+                      RtFloat4* sph9, float* r2, uint32_t* orig)
+{
+    const float  nan  = std::nanf("");
+    const float  ninf = -INFINITY;
+    const double B = (double)RT_CULL_B, m = (double)RT_CULL_M;
+    for (size_t g = 0; g < order.groups.size(); ++g) {
+        const std::vector<uint32_t>& idx = order.groups[g];
+        double cb[3] = {0, 0, 0};
+        for (uint32_t i : idx) { cb[0] += sph_filter[i].x; cb[1] += sph_filter[i].y; cb[2] += sph_filter[i].z; }
+        for (int a = 0; a < 3; ++a) cb[a] /= (double)idx.size();
+        const float cbf[3] = {(float)cb[0], (float)cb[1], (float)cb[2]};          // the centre the kernel uses
+        double rgeo = 0.0, cg = 0.0;
+        for (uint32_t i : idx) {
+            const double c[3] = {sph_filter[i].x, sph_filter[i].y, sph_filter[i].z};
+            const double r = std::sqrt((double)sph_r2[i]);
+            const double dx = c[0] - cbf[0], dy = c[1] - cbf[1], dz = c[2] - cbf[2];
+            rgeo = std::max(rgeo, std::sqrt(dx * dx + dy * dy + dz * dz) + r);
+            cg   = std::max(cg, std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) + r);
+        }
+        rgeo = rgeo * (1.0 + 1e-6) + 1e-30;
+        const double A   = rgeo + B * cg;
+        const double ccb = (double)cbf[0] * cbf[0] + (double)cbf[1] * cbf[1] + (double)cbf[2] * cbf[2];
+        const double w   = ccb - A * A - m * (ccb + A * A) - 1e-30;
+        const double gb  = 2.0 * A * B * (1.0 + m);
+        float wf = (float)w, gf = (float)gb;
+        if ((double)wf > w) wf = std::nextafterf(wf, ninf);
+        if ((double)gf < gb) gf = std::nextafterf(gf, INFINITY);
+        const bool usable = g >= order.always && std::isfinite(wf) && std::isfinite(gf) && std::isfinite(cbf[0]) &&
+                            std::isfinite(cbf[1]) && std::isfinite(cbf[2]);
+        bound[g] = usable ? RtFloat4{cbf[0], cbf[1], cbf[2], wf} : RtFloat4{0.f, 0.f, 0.f, ninf};   // -inf: always passes
+        for (size_t k = 0; k < 8; ++k) {
+            const bool real = k < idx.size();
+            sph9[9 * g + k] = real ? sph_filter[idx[k]] : RtFloat4{nan, nan, nan, nan};
+            r2[8 * g + k]   = real ? sph_r2[idx[k]] : nan;
+            orig[8 * g + k] = real ? idx[k] : 0xffffffffu;
+        }
+        sph9[9 * g + 8] = RtFloat4{usable ? gf : 0.f, 0.f, 0.f, 0.f};
+    }
+}
+}   // namespace
+
 // Scene pack: AoS {Sphere, Triangle} -> the SoA blob of rt_types.h.
 const World::Packed& World::packed() const
 {
@@ -219,6 +330,16 @@ const World::Packed& World::packed() const
     p->off_sph_filter = off; off += Sp * sizeof(RtFloat4);
     const size_t off_plane_b = off; off += Tp * sizeof(RtFloat4);
     p->off_sph_r2    = off; off += align_up(Sp * sizeof(float), 16);
+    // block C exists for the sphere counts the FILTER kernels serve; order and bounds first
+    CullOrder order;
+    if (S >= RT_FILTER_FROM) order = cull_order(spheres);
+    const size_t Gc = order.groups.size();
+    p->n_groups = (uint32_t)Gc;
+    p->off_cull_bound = off; off += Gc * sizeof(RtFloat4);
+    p->off_cull_sph   = off; off += 9 * Gc * sizeof(RtFloat4);
+    const size_t off_plane_c = off; off += Tp * sizeof(RtFloat4);
+    p->off_cull_r2    = off; off += align_up(8 * Gc * sizeof(float), 16);
+    p->off_cull_orig  = off; off += align_up(8 * Gc * sizeof(uint32_t), 16);
     p->off_tri_cull  = off; off += 3 * T * sizeof(RtFloat4);
     p->off_tri_v     = off; off += 3 * T * sizeof(RtFloat4);
     off = align_up(off, 32);
@@ -265,6 +386,13 @@ const World::Packed& World::packed() const
         triangle_cull_record(t, &cull[3 * j]);
     }
     std::memcpy(base + off_plane_b, plane, Tp * sizeof(RtFloat4));
+    std::memcpy(base + off_plane_c, plane, Tp * sizeof(RtFloat4));
+    if (Gc) build_cull_block(order, reinterpret_cast<const RtFloat4*>(base + p->off_sph_filter),
+                             reinterpret_cast<const float*>(base + p->off_sph_r2),
+                             reinterpret_cast<RtFloat4*>(base + p->off_cull_bound),
+                             reinterpret_cast<RtFloat4*>(base + p->off_cull_sph),
+                             reinterpret_cast<float*>(base + p->off_cull_r2),
+                             reinterpret_cast<uint32_t*>(base + p->off_cull_orig));
     packed_ = std::move(p);
     return *packed_;
 }

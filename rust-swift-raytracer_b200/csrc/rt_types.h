@@ -10,6 +10,14 @@
 //   [ sph_filter: float4 x Sp]  {cx, cy, cz, c.c - r*r - margin}  hot  (rt_trace.cuh, sphere_filter_group)
 //   [ tri_plane : float4 x Tp]  (same as in block A)              hot
 //   [ sph_r2    : float  x Sp]  r*r                               warm (filter survivors only)
+//   block C (staged instead of A/B by the CULL kernels: RT_FLAG_GROUP_CULL, an opt-in mode)
+//   [ cull_bound: float4 x Gc]  bounding sphere of a group of 8 spheres: {cB.xyz, wB}    hot
+//   [ cull_sph  : float4 x 9Gc] the spheres in spatial (Morton) order, 8 filter records
+//                               {c.xyz, c.c - r*r - margin} per group + one float4 {gB,0,0,0};
+//                               the 144-byte group stride spreads per-lane group reads over the banks   hot
+//   [ tri_plane : float4 x Tp]  (same as in block A)                                  hot
+//   [ cull_r2   : float  x 8Gc] r*r in the same order                                 warm
+//   [ cull_orig : u32    x 8Gc] list index of each sphere (hit-test order = tie-break order)  warm
 //   then
 //   [ tri_cull  : float4 x 3T]  {G2.xyz, g2}, {G0.xyz, g0}, {K,0,0,0}: approximate barycentric
 //                               gradients for the conservative edge-stage reject   warm (plane-stage survivors)
@@ -51,6 +59,13 @@ struct RtFloat4 { float x, y, z, w; };
 #define RT_FILTER_GROUP 8u     /* spheres per group of the FILTER kernels (a multiple of RT_SPHERE_GROUP) */
 #endif
 #define RT_FILTER_FROM  64u    /* sphere lists of at least this many run the FILTER kernels */
+/* How the spheres are walked (template parameter SPH of the kernels) */
+#define RT_SPH_DIRECT 0   /* the reference's test for every sphere */
+#define RT_SPH_FILTER 1   /* conservative 8-instruction filter first */
+#define RT_SPH_CULL   2   /* bounding spheres of groups first, then the filter, then the reference's test */
+/* constants of the group bound test (rt_trace.cuh cull_spheres, rt_scene.cpp build_cull_block) */
+#define RT_CULL_B   3.5e-3f                 /* >= sqrt(189 * 2^-24): growth of a member's effective radius with |o|+|c|+r */
+#define RT_CULL_M   3.0517578125e-05f       /* 2^-15: margin of the bound test's own evaluation */
 #define RT_TRI_GROUP    2u
 
 // Everything the shading step needs about the primitive that was hit: one 32-byte record,
@@ -70,6 +85,10 @@ struct RtSceneView {
     const RtFloat4*   tri_plane;  // [n_tri_pad]  block A
     const RtFloat4*   sph_filter; // [n_sph_pad]  block B (followed by tri_plane again, then sph_r2)
     const float*      sph_r2;     // [n_sph_pad]  block B
+    const RtFloat4*   cull_bound; // [n_groups]     block C
+    const RtFloat4*   cull_sph;   // [9*n_groups]   block C (followed by tri_plane again)
+    const float*      cull_r2;    // [8*n_groups]
+    const uint32_t*   cull_orig;  // [8*n_groups]
     const RtFloat4*   tri_cull;   // [3T]
     const RtFloat4*   tri_v;      // [3T]
     const RtPrimInfo* info;       // [S+T]
@@ -77,6 +96,8 @@ struct RtSceneView {
     uint32_t          n_sph_pad;  // multiple of RT_SPHERE_GROUP
     uint32_t          n_tri;
     uint32_t          n_tri_pad;  // multiple of RT_TRI_GROUP
+    uint32_t          n_groups;   // block C: groups of 8 spheres (0: the world has no block C)
+    uint32_t          pad;
 };
 
 // Row-tile sharding.  The frame's tiles (tile_rows image rows each, top to bottom) are dealt to
@@ -100,6 +121,7 @@ enum : uint32_t {
     RT_FLAG_ACCUM_OUT    = 1u << 2,   // write the float4 accumulator back
     RT_FLAG_NO_RESOLVE   = 1u << 3,   // skip the RGBA8 pack (intermediate progressive pass)
     RT_FLAG_COMPACT_OUT  = 1u << 4,   // out/accum hold only this shard's tiles, packed
+    RT_FLAG_GROUP_CULL   = 1u << 6,   // run the CULL kernels (block C): same hits, fewer sphere tests
     RT_FLAG_SAMPLE_ITEMS = 1u << 5,   // work items are (pixel, sample) pairs; colours go to `samples`, the
                                       // ordered sum + resolve is done by rt_resolve_samples_kernel
 };

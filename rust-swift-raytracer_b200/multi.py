@@ -160,7 +160,7 @@ class ShardedRenderer:
             self.frame_ptr = 0
 
     def render(self, spp: int, depth: int, passes: int = 1, seed: Optional[int] = None, fast_math: bool = False,
-               fixed_jitter: bool = False, to_host: bool = False, count_rays: bool = False):
+               fixed_jitter: bool = False, to_host: bool = False, count_rays: bool = False, group_cull: bool = False):
         """Returns (frame, rays).  frame: on rank 0 the [H, W] int32 RGBA8 frame — the pinned host
         tensor when to_host, else a device tensor (nccl gather) or the raw device address of the
         frame (peer gather); None on the other ranks.  rays: this rank's ray-segment count when
@@ -180,7 +180,7 @@ class ShardedRenderer:
             o = rt.Options(per, depth, sample_begin=p * per, resolve_spp=spp, fast_math=fast_math,
                            fixed_jitter=fixed_jitter, tile_rows=self.tile_rows, shard_index=self.rank,
                            shard_count=self.world, accum_in=p > 0, accum_out=not last, no_resolve=not last,
-                           full_frame_out=peer)
+                           full_frame_out=peer, group_cull=group_cull)
             if seed is not None:
                 o.seed = seed
             st = rt.RenderStats() if count_rays else None

@@ -21,6 +21,9 @@ for fast in (False, True):
     go("c3 filter", scenes.c3_world(), 24, 14, 1, 4, fast_math=fast)
     go("c5 filter+tris 1024", scenes.c5_world(), 16, 9, 1, 3, fast_math=fast)
     go("global path", scenes.synthetic_world(15000, 500, seed=77), 8, 5, 1, 2, fast_math=fast)
+    go("c3 cull", scenes.c3_world(), 24, 14, 1, 4, fast_math=fast, group_cull=True)
+    go("c5 cull+tris", scenes.c5_world(), 16, 9, 1, 3, fast_math=fast, group_cull=True)
+    go("global cull", scenes.synthetic_world(15000, 500, seed=77), 8, 5, 1, 2, fast_math=fast, group_cull=True)
 go("empty", "camera origin 0.0 0.0 0.0 aspect 1.5;", 9, 5, 2, 3)
 go("1x1", scenes.example_world(), 1, 1, 2, 3)
 print("selftest", rt.selftest_division(1 << 16, 1))

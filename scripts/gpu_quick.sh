@@ -16,6 +16,9 @@ run --workload c3 --steps 2 --warmup 3 --no-e2e
 run --workload c3 --steps 2 --warmup 3 --no-e2e --fast-math
 run --workload c5 --steps 2 --warmup 3 --no-e2e
 run --workload c5 --steps 2 --warmup 3 --no-e2e --fast-math
+run --workload c3 --steps 2 --warmup 3 --no-e2e --cull
+run --workload c3 --steps 2 --warmup 3 --no-e2e --cull --fast-math
+run --workload c5 --steps 2 --warmup 3 --no-e2e --cull
 if [ $# -ge 1 ]; then
   W=$1; shift
   CMD="python bench.py --workload $W --steps 1 --warmup 3 --no-cpu-baseline --no-e2e $*"

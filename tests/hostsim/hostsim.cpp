@@ -28,11 +28,13 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
 
     RtFrameParams P{};
     std::memcpy(&P.camera, cam12, sizeof(float) * 12);
-    P.width = W; P.height = H; P.spp = spp; P.depth = depth; P.seed = seed; P.flags = flags & 0x7fffffffu;   // bit 31: run the FILTER variant of the exact policy
+    P.width = W; P.height = H; P.spp = spp; P.depth = depth; P.seed = seed; P.flags = flags & 0x3fffffffu;   // bits 31/30 select the sphere-walk variant (below)
     P.wm1 = (float)(W - 1u); P.hm1 = (float)(H - 1u);
     P.sample_begin = sample_begin;
     P.resolve_spp  = resolve_spp ? resolve_spp : sample_begin + spp;
 
+    CullView cv{G.cull_bound, G.cull_sph, G.cull_r2, G.cull_orig, G.n_groups};
+    if ((flags & 0x40000000u) && G.n_groups == 0) return 100;      // the world has no block C (< 64 spheres)
     uint64_t rays = 0;
     uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
     const bool trace = spp > 0 && depth > 0;
@@ -41,10 +43,14 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
             Lane L{};
             begin_pixel(L, P, column, H - 1u - image_row, image_row * W + column);
             // the kernel's loop for one lane: one ray segment per iteration until the pixel is complete
-            while (trace && L.sample < spp) rays += 1, (void)((flags & 0x80000000u)
-                                                           ? trace_segment<false, true, true>(L, P, G, G.sph_filter, G.sph_r2, G.tri_plane)
-                                                           : (G.n_tri_pad ? trace_segment<false, false, true>(L, P, G, G.sph, nullptr, G.tri_plane)
-                                                                          : trace_segment<false, false, false>(L, P, G, G.sph, nullptr, G.tri_plane)));
+            // the kernel's loop for one lane; bit 31 of `flags` selects the FILTER variant, bit 30 the CULL variant
+            while (trace && L.sample < spp) {
+                ++rays;
+                if (flags & 0x40000000u)      trace_segment<false, RT_SPH_CULL, true>(L, P, G, G.sph_filter, G.sph_r2, cv, G.tri_plane);
+                else if (flags & 0x80000000u) trace_segment<false, RT_SPH_FILTER, true>(L, P, G, G.sph_filter, G.sph_r2, cv, G.tri_plane);
+                else if (G.n_tri_pad)         trace_segment<false, RT_SPH_DIRECT, true>(L, P, G, G.sph, nullptr, cv, G.tri_plane);
+                else                          trace_segment<false, RT_SPH_DIRECT, false>(L, P, G, G.sph, nullptr, cv, G.tri_plane);
+            }
             out32[L.out_index] = resolve_pixel<false>(L.acc_r, L.acc_g, L.acc_b, pixel_alpha(1.0f, spp > 0 ? spp : 0),
                                                       P.resolve_spp);
         }

@@ -216,6 +216,8 @@ def test_random_worlds_fuzz(gpu_rt, ob, seed):
     for items in (False, True):
         got, st = _render(rt, h, W, H, spp, depth, sample_items=items)
         assert st.filtered == 1 and st.rays == rays and np.array_equal(got, want), (seed, items)
+    got, st = _render(rt, h, W, H, spp, depth, group_cull=True)             # opt-in acceleration mode
+    assert st.culled == 1 and st.rays == rays and np.array_equal(got, want), seed
 
 
 def test_seed_changes_the_realisation_and_matches_oracle(gpu_rt, ob, scenes):
@@ -587,6 +589,27 @@ def test_one_process_per_gpu_sharded_frame_equals_single_gpu(gpu_rt, scenes, gat
     assert rays == st.rays
     assert np.array_equal(frame.view(np.uint8).reshape(170, 333, 4), want)
     assert np.array_equal(frame2, frame)
+
+
+@pytest.mark.parametrize("key,W,H,spp,depth", [("c3", 480, 270, 2, 8), ("c5", 96, 54, 2, 16), ("c5mini", 160, 90, 2, 16)])
+def test_group_cull_mode_is_bit_identical(gpu_rt, ob, scenes, key, W, H, spp, depth):
+    """RT_OPT_GROUP_CULL (opt-in): bounding spheres over spatially ordered groups of
+    8 spheres in front of the filter.  Same pixels, same ray counts, both kernels' sample scheduling;
+    worlds below 64 spheres ignore the flag."""
+    rt = gpu_rt
+    text = cases.scene_text(scenes, key)
+    h = rt.load_world(text)
+    cam, world = ob.parse_input(text)
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    for items in (False, True):
+        got, st = _render(rt, h, W, H, spp, depth, group_cull=True, sample_items=items)
+        assert st.culled == 1 and st.rays == rays and np.array_equal(got, want), (key, items)
+    fast_plain, sp = _render(rt, h, W, H, spp, depth, fast_math=True)
+    fast_cull, sc = _render(rt, h, W, H, spp, depth, fast_math=True, group_cull=True)
+    assert sc.culled == 1 and sc.rays == sp.rays and np.array_equal(fast_cull, fast_plain)   # same test decides
+    small = rt.load_world(scenes.default_world())
+    _, st = _render(rt, small, 64, 36, 2, 4, group_cull=True)
+    assert st.culled == 0
 
 
 def test_multi_gpu_tile_gather_when_two_devices(gpu_rt, scenes):

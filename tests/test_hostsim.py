@@ -40,6 +40,21 @@ def test_device_header_on_host_equals_oracle(hostsim, ob, scenes, case):
     assert np.array_equal(out, want)
 
 
+@pytest.mark.parametrize("key,W,H,spp,depth", [("c3", 64, 36, 2, 8), ("c5mini", 48, 27, 2, 16), ("c5", 24, 14, 1, 16)])
+def test_cull_variant_equals_oracle(hostsim, ob, scenes, key, W, H, spp, depth):
+    """RT_SPH_CULL: bounding spheres over spatially ordered groups of 8 in front of the filter —
+    same pixels, same ray counts (the list-order tie-break is carried by the stored list index)."""
+    cam, world = cases.oracle_scene(ob, scenes, key, "file")
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    out = np.zeros((H, W, 4), np.uint8)
+    n = C.c_uint64()
+    cf = cam.floats()
+    rc = hostsim.hostsim_render(cases.scene_text(scenes, key).encode(), cf.ctypes.data_as(C.POINTER(C.c_float)), W, H,
+                                spp, depth, ob.SEED_DEFAULT, 0x40000000, 0, 0, out.ctypes.data, C.byref(n))
+    assert rc == 0 and n.value == rays
+    assert np.array_equal(out, want)
+
+
 @pytest.mark.parametrize("key,W,H,spp,depth", [("c3", 64, 36, 2, 8), ("c5mini", 48, 27, 2, 16), ("example", 80, 80, 3, 8)])
 def test_filter_variant_of_the_exact_policy_equals_oracle(hostsim, ob, scenes, key, W, H, spp, depth):
     """The conservative FMA sphere filter (block B, sphere_filter_group) in front of the exact
@@ -66,7 +81,7 @@ def test_random_worlds_through_the_filters(hostsim, ob, seed):
     W, H, spp, depth = 40, 28, 2, 6
     want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
     cf = cam.floats()
-    for flags in (0, 0x80000000):                     # direct loops, FILTER variant
+    for flags in (0, 0x80000000, 0x40000000):         # direct loops, FILTER variant, CULL variant
         out = np.zeros((H, W, 4), np.uint8)
         n = C.c_uint64()
         rc = hostsim.hostsim_render(text.encode(), cf.ctypes.data_as(C.POINTER(C.c_float)), W, H, spp, depth,
