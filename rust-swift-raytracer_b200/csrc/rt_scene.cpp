@@ -278,6 +278,12 @@ void build_cull_block(const CullOrder& order, const RtFloat4* sph_filter, const 
     const double B = (double)RT_CULL_B, m = (double)RT_CULL_M;
     for (size_t g = 0; g < order.groups.size(); ++g) {
         const std::vector<uint32_t>& idx = order.groups[g];
+        if (idx.empty()) {                                     // padding group: never passes, never hit
+            bound[g] = RtFloat4{nan, nan, nan, nan};
+            for (size_t k = 0; k < 8; ++k) { sph9[9 * g + k] = RtFloat4{nan, nan, nan, nan}; r2[8 * g + k] = nan; orig[8 * g + k] = 0xffffffffu; }
+            sph9[9 * g + 8] = RtFloat4{0.f, 0.f, 0.f, 0.f};
+            continue;
+        }
         double cb[3] = {0, 0, 0};
         for (uint32_t i : idx) { cb[0] += sph_filter[i].x; cb[1] += sph_filter[i].y; cb[2] += sph_filter[i].z; }
         for (int a = 0; a < 3; ++a) cb[a] /= (double)idx.size();
@@ -333,6 +339,7 @@ const World::Packed& World::packed() const
     // block C exists for the sphere counts the FILTER kernels serve; order and bounds first
     CullOrder order;
     if (S >= RT_FILTER_FROM) order = cull_order(spheres);
+    while (order.groups.size() % 32u) order.groups.emplace_back();     // whole rounds of 32 groups (empty = NaN groups)
     const size_t Gc = order.groups.size();
     p->n_groups = (uint32_t)Gc;
     p->off_cull_bound = off; off += Gc * sizeof(RtFloat4);
