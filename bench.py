@@ -239,6 +239,10 @@ def main():
     if args.warmup is None:
         args.warmup = 3 if heavy else 5
 
+    if args.impl != "reference":
+        args.warmup = max(args.warmup, 3)            # timing rule: at least 3 untimed warm-up steps
+    args.steps = max(args.steps, 1)
+
     scenes = importlib.import_module("rust-swift-raytracer_b200.scenes")
     if args.impl == "reference":
         return run_reference(args, scenes)
