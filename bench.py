@@ -172,12 +172,12 @@ def run_reference(args, scenes):
     wl = WORKLOADS[args.workload]
     desc, key, W, H, spp, depth, _ = wl
     cam, world = ob.parse_input(scene_text(scenes, key))
-    # one step = the full frame at `s` spp, sized so that (K + W) steps take <= ~150 s
+    # one step = the full frame at `s` spp, sized so that (K + W) steps take <= ~60 s
     probe_h = max(2, H // 16)
     t = time.perf_counter()
     ob.ray_trace(world, cam, W, probe_h, 1, depth, rng_mode=ob.RNG_SERIAL, threads=1)
     per_spp = (time.perf_counter() - t) * (H / probe_h)
-    s = int(max(1, min(spp, 150.0 / max(per_spp * (args.steps + args.warmup), 1e-6))))
+    s = int(max(1, min(spp, 60.0 / max(per_spp * (args.steps + args.warmup), 1e-6))))
     for _ in range(args.warmup):
         ob.ray_trace(world, cam, W, H, s, depth, rng_mode=ob.RNG_SERIAL, threads=1)
     rays_total, t0 = 0, time.perf_counter()
