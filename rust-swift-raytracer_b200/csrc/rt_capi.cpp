@@ -126,7 +126,7 @@ static Rust_WorldHandle* load_world_impl(const char* source, bool allow_emission
             return nullptr;
         }
         auto* h   = new Rust_WorldHandle;
-        h->world  = new Rust_World{std::move(r.world)};
+        h->world  = new Rust_World{std::move(r.world), Progressive{}};
         h->camera = new Rust_Camera{r.camera};
         return h;
     } catch (const std::exception& e) {
@@ -315,7 +315,7 @@ Rust_WorldHandle* rt_world_new(const float origin[3], float aspect)
 {
     clear_error();
     auto* h   = new Rust_WorldHandle;
-    h->world  = new Rust_World{rt::World::make({}, {})};
+    h->world  = new Rust_World{rt::World::make({}, {}), Progressive{}};
     h->camera = new Rust_Camera{rt::Camera::new_at(origin ? RtVec3{origin[0], origin[1], origin[2]} : RtVec3{0, 0, 0}, aspect)};
     return h;
 }
