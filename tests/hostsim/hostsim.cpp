@@ -7,7 +7,9 @@
 #include "../../rust-swift-raytracer_b200/csrc/rt_trace.cuh"
 #include "../../rust-swift-raytracer_b200/csrc/rt_host.hpp"
 
+#include <cmath>
 #include <cstring>
+#include <vector>
 
 namespace rt {
 struct DeviceScene {};
@@ -55,5 +57,54 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
                                                       P.resolve_spp);
         }
     if (rays_out) *rays_out = rays;
+    return 0;
+}
+
+// TEST-ONLY: structural invariants of block C (rt_scene.cpp build_cull_block), independent of any render:
+//  * every sphere of the list appears exactly once among the group members (cull_orig);
+//  * a member's filter record and r*r are the list's own;
+//  * the stored bound constants dominate  A = |c_k - cB| + r_k + B(|c_k| + r_k)  for every member,
+//    where A is recovered from gB = 2AB(1+m)  (groups with wB = -inf always pass and are exempt).
+// Returns 0 when all hold, otherwise a code; *n_groups_out / *n_always_out describe the block.
+extern "C" int hostsim_check_cull(const char* scene_text, uint32_t* n_groups_out, uint32_t* n_always_out)
+{
+    using namespace rt;
+    ParseResult pr = parse_input(scene_text, std::strlen(scene_text));
+    if (pr.error != ParseError::Ok) return (int)pr.error;
+    const World::Packed& pk = pr.world->packed();
+    RtSceneView G = pk.view(pk.blob.data());
+    if (n_groups_out) *n_groups_out = G.n_groups;
+    if (G.n_groups == 0) return G.n_sph >= RT_FILTER_FROM ? 101 : 0;
+    if (G.n_groups % 32u) return 102;
+    std::vector<uint32_t> seen(G.n_sph, 0);
+    uint32_t always = 0;
+    for (uint32_t g = 0; g < G.n_groups; ++g) {
+        const RtFloat4 b  = G.cull_bound[g];
+        const float    gb = G.cull_sph[9u * g + 8u].x;
+        const bool pass_always = std::isinf(b.w) && b.w < 0;
+        if (pass_always) ++always;
+        const double A = (double)gb / (2.0 * (double)RT_CULL_B * (1.0 + (double)RT_CULL_M));
+        for (uint32_t k = 0; k < 8; ++k) {
+            const uint32_t idx = G.cull_orig[8u * g + k];
+            const RtFloat4 s   = G.cull_sph[9u * g + k];
+            if (idx == 0xffffffffu) { if (s.x == s.x) return 103; continue; }      // padding must be NaN
+            if (idx >= G.n_sph) return 104;
+            ++seen[idx];
+            if (std::memcmp(&s, &G.sph_filter[idx], sizeof s) != 0) return 105;
+            if (std::memcmp(&G.cull_r2[8u * g + k], &G.sph_r2[idx], sizeof(float)) != 0) return 106;
+            if (pass_always) continue;
+            const double c[3] = {s.x, s.y, s.z}, r = std::sqrt((double)G.sph_r2[idx]);
+            const double dx = c[0] - b.x, dy = c[1] - b.y, dz = c[2] - b.z;
+            const double need = std::sqrt(dx * dx + dy * dy + dz * dz) + r +
+                                (double)RT_CULL_B * (std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) + r);
+            if (!(A >= need * (1.0 - 1e-9))) return 107;
+            // wB = cB.cB - A^2 - m(cB.cB + A^2), rounded down: must not exceed the exact value
+            const double ccb = (double)b.x * b.x + (double)b.y * b.y + (double)b.z * b.z;
+            if (!((double)b.w <= ccb - A * A * (1.0 - 1e-6))) return 108;
+        }
+    }
+    for (uint32_t i = 0; i < G.n_sph; ++i)
+        if (seen[i] != 1) return 109;
+    if (n_always_out) *n_always_out = always;
     return 0;
 }

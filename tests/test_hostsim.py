@@ -20,7 +20,22 @@ def hostsim():
     L.hostsim_render.restype = C.c_int
     L.hostsim_render.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.c_int32, C.c_int32,
                                  C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.hostsim_check_cull.restype = C.c_int
+    L.hostsim_check_cull.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     return L
+
+
+def test_cull_block_invariants(hostsim, scenes):
+    """Block C of the scene blob (group-cull mode): every sphere exactly once, member records are the
+    list's own, and every group's bound constants dominate what the derivation in rt_trace.cuh needs."""
+    for text, want_groups in ((scenes.c3_world(), True), (scenes.c5_world(), True), (scenes.default_world(), False),
+                              (cases.random_world(3, n_spheres=300), True), (cases.random_world(4, n_spheres=64), True)):
+        ng, na = C.c_uint32(), C.c_uint32()
+        assert hostsim.hostsim_check_cull(text.encode(), C.byref(ng), C.byref(na)) == 0
+        assert (ng.value > 0) == want_groups and ng.value % 32 == 0
+    # the C3 scene's ground sphere (r = 1000) sits in a group of its own that always passes
+    ng, na = C.c_uint32(), C.c_uint32()
+    assert hostsim.hostsim_check_cull(scenes.c3_world().encode(), C.byref(ng), C.byref(na)) == 0 and na.value == 1
 
 
 @pytest.mark.parametrize("case", cases.SMALL_CASES, ids=[c[0] for c in cases.SMALL_CASES])
