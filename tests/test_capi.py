@@ -58,6 +58,24 @@ def test_reference_header_is_source_compatible(tmp_path):
     assert subprocess.run([str(exe)]).returncode == 0
 
 
+def test_additive_header_is_strict_c_and_cxx(tmp_path):
+    """include/raytracer_b200.h (plain pointers and sizes only) compiles as pedantic C11 and as C++17."""
+    import subprocess
+    src = tmp_path / "use.c"
+    src.write_text('#include "raytracer_b200.h"\n'
+                   "int main(void) {\n"
+                   "  RtRenderOptions o; RtRenderStats s; (void)s;\n"
+                   "  o.struct_size = (uint32_t)sizeof o; o.flags = RT_OPT_FIXED_JITTER | RT_OPT_GROUP_CULL;\n"
+                   "  return rt_abi_version() == RT_B200_ABI_VERSION && o.flags ? 0 : 1; }\n")
+    lib = ROOT / "rust-swift-raytracer_b200" / "lib"
+    for cc, std in (("/usr/bin/gcc", ["-std=c11", "-pedantic"]), ("/usr/bin/g++", ["-std=c++17", "-x", "c++"])):
+        exe = tmp_path / ("use_" + Path(cc).name.replace("+", "p"))
+        r = subprocess.run([cc] + std + ["-Wall", "-Wextra", "-Werror", f"-I{ROOT / 'include'}", str(src), f"-L{lib}",
+                            "-lraytracer", f"-Wl,-rpath,{lib}", "-o", str(exe)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert subprocess.run([str(exe)]).returncode == 0
+
+
 def test_move_camera_position_lib_rs_60(rt, ob, scenes):
     h = rt.load_world(scenes.default_world())
     h.set_camera_look_at((1, 2, 3), (0, 0, -1), (0, 1, 0), 0.8, 1.5)
