@@ -29,7 +29,6 @@ from __future__ import annotations
 import argparse
 import importlib
 import json
-import math
 import os
 import sys
 import threading
