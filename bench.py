@@ -11,14 +11,20 @@ call (common.rs:268), counted by the kernel itself.
   N = 1 : BASELINE config 2 — default scene, 1920x1080, 64 spp, depth 8 — one persistent
           render-kernel launch per step.
   N > 1 : BASELINE config 4 — default scene, 3840x2160, 1,024 spp as 16 progressive passes of
-          64 spp, the frame sharded by 16-row tiles across the ranks (tile t -> rank t % N), the
-          finished RGBA8 tiles gathered to rank 0 over NCCL/NVLink (the only collective).
-          Strong scaling: the frame is fixed, N GPUs split it.
+          64 spp (fused into one persistent launch per GPU), the frame sharded by 16-row tiles across
+          the ranks (stripes of N tiles dealt alternately forwards and backwards, rt_shard_tile; the
+          tail of the frame is stolen across GPUs over NVLink), the finished RGBA8 tiles stored by the
+          render kernels into rank 0's frame over NVLink (the only exchange).
+          Strong scaling: the frame is fixed, N GPUs split it.  The line carries, measured in the same
+          run, the 1-GPU time of the same frame (`strong_scaling`) and `parity` (sha256 of the gathered
+          frame == sha256 of the single-GPU frame, ray counts equal); a mismatch makes the run fail.
 
 `value`  : rays/s with everything resident in HBM, timed with CUDA events on the launching
            stream, L2 flushed (256 MiB write) between steps outside the events, max over ranks.
-`e2e`    : the same frame through the reference-facing C-ABI call with a HOST framebuffer
-           (render_with_options -> D2H of the finished frame inside the timed region).
+`e2e`    : the same frame through the reference-facing C-ABI call with a PAGEABLE host framebuffer
+           (render_with_options; what the reference's callers pass), the frame's way to the host inside
+           the timed region; `e2e_pinned` is the same with an rt_alloc_pixels buffer.
+`workloads` (N = 1 default line): C3, C5 and C4-on-one-GPU timed the same way, each with its roofline.
 `roofline`: FP32 CUDA-core roofline (no tensor-core work exists on this path): algorithmic
            flops (DESIGN.md / SURVEY.md §8d) / kernel time / FFMA peak measured in this run.
 The default kernel is the bit-exact one (IEEE arithmetic in the reference's association order,
@@ -195,7 +201,8 @@ def run_reference(args, scenes):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "note": "rays/s is independent of spp; frame time scales linearly in spp"},
+            "config": {"workload": desc, "sample": f"each step renders {s} of the workload's {spp} spp (full frame, full depth)",
+                       "note": "rays/s is independent of spp; frame time scales linearly in spp"},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": "port", "sample": sample,
                              "all_cores": {"value": rays_mt / dt_mt / 1e6, "cores": ncores,
                                            "note": "oracle per-sample-RNG mode with OpenMP over rows"}},
@@ -206,6 +213,68 @@ def run_reference(args, scenes):
 
 
 # ---------------------------------------------------------------------------------- GPU arm
+
+def _events(torch, n):
+    return [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+
+
+def time_workload_1gpu(torch, rt, multi, scenes, key, dev, flush, steps, warmup, fast=False, cull=False, fp32_peak=0.0):
+    """Device-timed rays/s of one workload on ONE GPU (this rank's), same method as the headline: CUDA events
+    on the launching stream around every step, L2 flushed in between.  Used for the `workloads` record of the
+    N = 1 line and for the in-run single-GPU base of the N > 1 lines."""
+    desc, skey, W, H, spp, depth, passes = WORKLOADS[key]
+    handle = rt.load_world(scene_text(scenes, skey))
+    r = multi.ShardedRenderer(rt, handle, W, H, 0, 1, tile_rows=16, device=dev)
+    st = rt.RenderStats()
+    frame, rays = r.render(spp, depth, passes, fast_math=fast, count_rays=True, group_cull=cull, stats=st)
+    for _ in range(max(warmup - 1, 0)):
+        flush.zero_()
+        r.render(spp, depth, passes, fast_math=fast, group_cull=cull)
+    torch.cuda.synchronize()
+    ev = _events(torch, steps)
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        frame, _ = r.render(spp, depth, passes, fast_math=fast, group_cull=cull)
+        b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    sha = __import__("hashlib").sha256(frame.cpu().numpy().tobytes()).hexdigest()
+    S, T = handle.n_spheres, handle.n_triangles
+    flops = algorithmic_flops(rays, W * H * spp, W * H, S, T)
+    achieved = flops / (ms * 1e-3) / 1e12
+    rec = {"workload": desc, "ms_per_step": ms, "value": rays / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "steps": steps,
+           "rays_per_step": int(rays), "launches_per_step": int(st.launches), "passes_fused": int(st.passes_fused),
+           "sample_items": int(st.sample_items), "kernel": "fast-math" if fast else "exact",
+           "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                        "frac": achieved / fp32_peak if fp32_peak else None, "flops_per_step": flops}}
+    r.close()
+    return rec, sha, int(rays)
+
+
+def ppm_record(rt, torch, dev):
+    """the step right after the path in the CLI and the example (image.rs:59-81) — writing
+    a 3840x2160 frame as ASCII P3 (the reference's format) and as binary P6, to tmpfs when there is one."""
+    import tempfile
+    W, H = 3840, 2160
+    fb = rt.Framebuffer(W, H)
+    fb.pixels[...] = (torch.arange(W * H * 4, dtype=torch.int64) * 2654435761 >> 13).to(torch.uint8).numpy().reshape(H, W, 4)
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    out = {}
+    for name, binary in (("p3", False), ("p6", True)):
+        path = os.path.join(d, f"rt_bench_{os.getpid()}_{name}.ppm")
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            rt.write_image(fb, path, binary=binary)
+            best = min(best, time.perf_counter() - t0)
+        size = os.path.getsize(path)
+        os.unlink(path)
+        out[name] = {"ms": best * 1e3, "bytes": size, "MB_per_s": size / best / 1e6, "Mpixels_per_s": W * H / best / 1e6}
+    out["frame"] = f"{W}x{H}"
+    out["dir"] = d
+    return out
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -220,16 +289,21 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N > 1: 'peer' = render kernels store their tiles into rank 0's frame over NVLink "
                          "(CUDA IPC mapping); 'nccl' = compact buffers + one dist.gather")
+    ap.add_argument("--no-steal", action="store_true", help="N > 1: static tile deal only (no cross-GPU work stealing)")
     ap.add_argument("--devices", type=int, default=0,
-                    help="N = 1 launch only: e2e through render_with_options(n_devices=D), ONE process driving D GPUs "
+                    help="N = 1 launch only: also time render_with_options(n_devices=D), ONE process driving D GPUs "
                          "(the shape the C-ABI callers have); reported under e2e_one_process")
     ap.add_argument("--cull", action="store_true",
                     help="opt-in acceleration mode (RT_OPT_GROUP_CULL): same frame, fewer sphere tests — a separately "
                          "reported mode, NOT the brute-force path the BASELINE metric is defined on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra records (N = 1: workloads c3/c5/c4, ppm; N > 1: single-GPU base + parity, "
+                         "one-process C-ABI e2e)")
     args = ap.parse_args()
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    default_line = args.workload is None and not args.spp and not args.fast_math and not args.cull
     if args.workload is None:
         args.workload = "c2" if max(args.gpus, world_size) == 1 else "c4"
     heavy = args.workload in ("c3", "c4")
@@ -246,6 +320,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args, scenes)
 
+    import hashlib
+    import numpy as np
     import torch
     import torch.distributed as dist
     build = importlib.import_module("rust-swift-raytracer_b200.build")
@@ -273,7 +349,8 @@ def main():
     handle = rt.load_world(scene_text(scenes, key))
     S, T = handle.n_spheres, handle.n_triangles
     dev = torch.device("cuda", local_rank)
-    renderer = multi.ShardedRenderer(rt, handle, W, H, rank, n_gpus, tile_rows=16, device=dev, gather=args.gather)
+    renderer = multi.ShardedRenderer(rt, handle, W, H, rank, n_gpus, tile_rows=16, device=dev, gather=args.gather,
+                                     steal=not args.no_steal)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -293,22 +370,24 @@ def main():
     fp32_peak = rt.measure_fp32_peak(local_rank) if rank == 0 else 0.0
 
     # ---- warm-up (first step also counts the rays of one frame; the frame is deterministic) ----
-    _, rays_local = renderer.render(spp, depth, passes, fast_math=fast, count_rays=True, group_cull=args.cull)
+    st0 = rt.RenderStats()
+    _, rays_local = renderer.render(spp, depth, passes, fast_math=fast, count_rays=True, group_cull=args.cull, stats=st0)
     rays_frame = allreduce(float(rays_local), dist.ReduceOp.SUM if n_gpus > 1 else None)
+    stolen_first = allreduce(float(st0.stolen_slots), dist.ReduceOp.SUM if n_gpus > 1 else None)
     for _ in range(max(args.warmup - 1, 0)):
         flush.zero_()
         renderer.render(spp, depth, passes, fast_math=fast, group_cull=args.cull)
     barrier()
 
     # ---- timed region: K steps, CUDA events on the launching stream around every step ----
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = _events(torch, args.steps)
     with ClockSampler(local_rank) as clocks:
         barrier()
         t_wall = time.perf_counter()
         for a, b in ev:
             flush.zero_()                       # L2 flush, outside the events
             a.record()
-            renderer.render(spp, depth, passes, fast_math=fast, group_cull=args.cull)
+            frame_dev, _ = renderer.render(spp, depth, passes, fast_math=fast, group_cull=args.cull)
             b.record()
         barrier()
         t_wall = time.perf_counter() - t_wall
@@ -317,45 +396,117 @@ def main():
     ms_per_step = dev_ms / args.steps
     value = rays_frame / (ms_per_step * 1e-3) / 1e6
 
-    # ---- e2e: host framebuffer through the public API, D2H inside the timed region ----
-    e2e = None
-    if not args.no_e2e:
-        if n_gpus == 1:
-            fb = rt.Framebuffer(W, H, pinned=True)
-            opts = rt.Options(spp, depth, fast_math=fast, group_cull=args.cull)
-
-            def e2e_step():
-                if passes == 1:
-                    rt.render_with_options(fb, handle, opts)     # the reference-facing C-ABI call
-                else:
-                    renderer.render(spp, depth, passes, fast_math=fast, to_host=True, group_cull=args.cull)
+    # sha256 of the frame of the last timed step (rank 0; N > 1: the gathered frame in rank 0's memory)
+    frame_sha = None
+    if rank == 0:
+        if renderer.gather == "peer" and n_gpus > 1:
+            host = torch.empty((H, W), dtype=torch.int32).pin_memory()
+            rt.copy_to_host(host.data_ptr(), frame_dev, W * H * 4, torch.cuda.current_stream(dev).cuda_stream)
+            torch.cuda.synchronize()
+            frame_sha = hashlib.sha256(host.numpy().tobytes()).hexdigest()
         else:
-            def e2e_step():
-                renderer.render(spp, depth, passes, fast_math=fast, to_host=True, group_cull=args.cull)
-        e2e_step()
+            frame_sha = hashlib.sha256(frame_dev.cpu().numpy().tobytes()).hexdigest()
+    barrier()
+
+    # ---- e2e: HOST framebuffer through the public API, host<->device traffic inside the timed region ----
+    def time_calls(fn, steps):
+        fn()
         barrier()
         tot = 0.0
-        for _ in range(args.steps):
+        for _ in range(steps):
             flush.zero_()
             barrier()
             t0 = time.perf_counter()
-            e2e_step()
+            fn()
             torch.cuda.synchronize()
             tot += allreduce(time.perf_counter() - t0, dist.ReduceOp.MAX if n_gpus > 1 else None)
-        e2e = {"value": rays_frame / (tot / args.steps) / 1e6, "unit": "Mrays/s",
-               "ms_per_frame": tot / args.steps * 1e3,
-               "h2d_bytes_per_step": 232 * passes,      # camera + frame parameters travel as kernel arguments
-               # (sizeof RtFrameParams + RtSceneView = 160 + 72);
-               # the scene blob is uploaded once by load_world (the reference's API has the same split)
-               "d2h_bytes_per_step": W * H * 4,
-               "api": "render_with_options (C ABI, pinned host framebuffer: the kernel stores the finished pixels "
-                      "straight into it over PCIe, no separate D2H copy)" if (n_gpus == 1 and passes == 1)
-                      else f"multi.ShardedRenderer.render(to_host=True): tile shards -> {renderer.gather} gather -> D2H on rank 0"}
+        return tot / steps
+
+    e2e = e2e_pinned = None
+    h2d = 360 + 112                               # RtFrameParams + RtSceneView travel as kernel arguments; the scene
+    # blob is uploaded once by load_world (the reference's API has the same split: load_world, then render)
+    if not args.no_e2e:
+        if n_gpus == 1:
+            opts = rt.Options(spp, depth, fast_math=fast, group_cull=args.cull, passes=passes)
+            fb_page = rt.Framebuffer(W, H, pinned=False)       # plain malloc'ed pixels: what the reference's callers
+            fb_pin = rt.Framebuffer(W, H, pinned=True)         # pass (GameView.swift:125-129, c_raytracer.rs:53)
+            t = time_calls(lambda: rt.render_with_options(fb_page, handle, opts), args.steps)
+            e2e = {"value": rays_frame / t / 1e6, "unit": "Mrays/s", "ms_per_frame": t * 1e3,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 4,
+                   "api": "render_with_options (C ABI), PAGEABLE host framebuffer (np.zeros / malloc): the kernel stores "
+                          "its pixels into the library's pinned staging frame over PCIe while it renders, then one memcpy "
+                          "into the caller's buffer"}
+            t = time_calls(lambda: rt.render_with_options(fb_pin, handle, opts), args.steps)
+            e2e_pinned = {"value": rays_frame / t / 1e6, "unit": "Mrays/s", "ms_per_frame": t * 1e3,
+                          "api": "render_with_options (C ABI), pinned framebuffer from rt_alloc_pixels: pixels stored straight "
+                                 "into the caller's buffer, no copy at all"}
+            assert np.array_equal(fb_page.pixels, fb_pin.pixels)
+        else:
+            t = time_calls(lambda: renderer.render(spp, depth, passes, fast_math=fast, to_host=True, group_cull=args.cull),
+                           args.steps)
+            e2e = {"value": rays_frame / t / 1e6, "unit": "Mrays/s", "ms_per_frame": t * 1e3,
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 4,
+                   "api": f"multi.ShardedRenderer.render(to_host=True): one process per GPU, tile shards -> {renderer.gather} "
+                          "gather -> one D2H on rank 0 into pinned host memory"}
+
+    # ---- extras (outside the headline timing) ----
+    extras = {}
+    if not args.no_extras and default_line:
+        if n_gpus == 1:
+            wls = {}
+            for k, steps_k in (("c3", 3), ("c5", 5), ("c4", 3)):
+                rec, _, _ = time_workload_1gpu(torch, rt, multi, scenes, k, dev, flush, steps_k, 3, fp32_peak=fp32_peak)
+                wls[k if k != "c4" else "c4_1gpu"] = rec
+            extras["workloads"] = wls
+            try:
+                extras["ppm"] = ppm_record(rt, torch, dev)
+            except Exception as e:      # noqa: BLE001
+                extras["ppm"] = {"error": repr(e)}
+        else:
+            # the SAME frame on one GPU, in this run: the base of the strong-scaling figure and the parity check
+            base = None
+            if rank == 0:
+                rec, sha1, rays1 = time_workload_1gpu(torch, rt, multi, scenes, args.workload, dev, flush, 2, 3,
+                                                      fp32_peak=fp32_peak)
+                base = (rec, sha1, rays1)
+            barrier()
+            if rank == 0:
+                rec, sha1, rays1 = base
+                extras["strong_scaling"] = {"base_ms_1gpu": rec["ms_per_step"], "base_value_1gpu": rec["value"],
+                                            "speedup": rec["ms_per_step"] / ms_per_step,
+                                            "note": "1-GPU base = the same frame rendered by rank 0 alone in this run "
+                                                    "(2 timed steps after 3 warm-ups, same timing method)"}
+                extras["parity"] = {"frame_sha256": frame_sha, "single_gpu_sha256": sha1,
+                                    "equals_single_gpu": frame_sha == sha1,
+                                    "rays": int(rays_frame), "single_gpu_rays": rays1, "rays_equal": int(rays_frame) == rays1}
+            # one process driving all N GPUs through the C ABI (what a caller of render_with_options gets)
+            if rank == 0:
+                try:
+                    fbm = rt.Framebuffer(W, H, pinned=False)
+                    om = rt.Options(spp, depth, fast_math=fast, n_devices=n_gpus, passes=passes)
+                    stm = rt.RenderStats()
+                    rt.render_with_options(fbm, handle, om, stm)
+                    tot = 0.0
+                    for _ in range(3):
+                        t0 = time.perf_counter()
+                        rt.render_with_options(fbm, handle, om)
+                        tot += time.perf_counter() - t0
+                    sham = hashlib.sha256(np.ascontiguousarray(fbm.pixels).tobytes()).hexdigest()
+                    extras["e2e_one_process"] = {
+                        "devices": int(stm.devices), "peer_gather": int(stm.peer_gather), "stolen_slots": int(stm.stolen_slots),
+                        "passes_fused": int(stm.passes_fused), "value": rays_frame / (tot / 3) / 1e6, "unit": "Mrays/s",
+                        "ms_per_frame": tot / 3 * 1e3, "d2h_bytes_per_step": W * H * 4,
+                        "equals_multi_process_frame": sham == frame_sha,
+                        "api": "render_with_options(n_devices=N, passes) — C ABI, ONE process drives the N GPUs (peer access), "
+                               "pageable host framebuffer"}
+                except Exception as e:      # noqa: BLE001
+                    extras["e2e_one_process"] = {"error": repr(e)}
+            barrier()
 
     one_process = None
-    if args.devices > 1 and n_gpus == 1 and passes == 1:
-        fbm = rt.Framebuffer(W, H, pinned=True)
-        om = rt.Options(spp, depth, fast_math=fast, n_devices=args.devices, group_cull=args.cull)
+    if args.devices > 1 and n_gpus == 1:
+        fbm = rt.Framebuffer(W, H, pinned=False)
+        om = rt.Options(spp, depth, fast_math=fast, n_devices=args.devices, group_cull=args.cull, passes=passes)
         stm = rt.RenderStats()
         rt.render_with_options(fbm, handle, om, stm)
         tot = 0.0
@@ -363,11 +514,14 @@ def main():
             t0 = time.perf_counter()
             rt.render_with_options(fbm, handle, om)
             tot += time.perf_counter() - t0
-        one_process = {"devices": int(stm.devices), "peer_gather": int(stm.peer_gather),
+        one_process = {"devices": int(stm.devices), "peer_gather": int(stm.peer_gather), "stolen_slots": int(stm.stolen_slots),
                        "value": rays_frame / (tot / args.steps) / 1e6, "unit": "Mrays/s",
                        "ms_per_frame": tot / args.steps * 1e3, "d2h_bytes_per_step": W * H * 4,
+                       "frame_sha256": hashlib.sha256(np.ascontiguousarray(fbm.pixels).tobytes()).hexdigest(),
                        "api": "render_with_options(n_devices=D): one process, tiles stored into device 0's frame "
                               "over NVLink peer mappings, one D2H"}
+    steal_on = bool(renderer.steal)
+    gather = renderer.gather
     renderer.close()
     if rank != 0:
         if n_gpus > 1:
@@ -377,24 +531,31 @@ def main():
     samples = W * H * spp
     flops = algorithmic_flops(rays_frame, samples, W * H, S, T)
     achieved = flops / (ms_per_step * 1e-3) / 1e12
+    launches_per_step = int(st0.launches)
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if n_gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "spheres": S, "triangles": T, "rays_per_step": int(rays_frame),
                    "samples_per_step": samples, "kernel": "fast-math" if fast else "exact (bit-identical to the oracle)",
+                   "passes": (f"{passes} progressive passes of {spp // passes} spp fused into one persistent launch "
+                              "(float4 sums through HBM between passes)") if passes > 1 else "1",
                    "sphere_walk": ("group-cull (opt-in acceleration: the roofline fraction below still counts the brute-force "
                                    "algorithmic flops, so it is a speed-up measure, not a pipe utilisation)") if args.cull
                                   else "brute force over the list (filtered for >= 64 spheres)",
-                   "parallelism": (f"row-tile shards x{n_gpus}, {renderer.gather} gather to rank 0 "
+                   "parallelism": (f"row-tile shards x{n_gpus} (static boustrophedon deal"
+                                   + (" + cross-GPU work stealing of the tail over NVLink atomics" if steal_on else "")
+                                   + f"), {gather} gather to rank 0 "
                                    + ("(tiles stored by the render kernels into rank 0's frame over NVLink, CUDA IPC)"
-                                      if renderer.gather == "peer" else "(compact buffers + dist.gather)"))
+                                      if gather == "peer" else "(compact buffers + dist.gather)"))
                    if n_gpus > 1 else "1 GPU",
+                   "stolen_slots_first_step": int(stolen_first) if n_gpus > 1 else 0,
                    "l2": "flushed between steps (256 MiB write, outside the CUDA events)",
                    "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
+                   "frame_sha256": frame_sha,
                    },
         "e2e": e2e,
-        "gpu_launches": args.steps * passes,
+        "gpu_launches": args.steps * launches_per_step * n_gpus,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak * n_gpus, "unit": "TFLOP/s",
                      "frac": achieved / (fp32_peak * n_gpus) if fp32_peak else None,
                      "traffic": NCU_TRAFFIC_BYTES.get((args.workload, fast)) if (n_gpus == 1 and not args.spp) else None,
@@ -406,6 +567,9 @@ def main():
                      "ncu_context": NCU_CONTEXT.get((args.workload, fast)) if n_gpus == 1 else None},
         "clocks": clocks.summary(),
     }
+    if e2e_pinned:
+        line["e2e_pinned"] = e2e_pinned
+    line.update(extras)
     if one_process:
         line["e2e_one_process"] = one_process
     if not args.no_cpu_baseline and n_gpus == 1:
@@ -413,6 +577,10 @@ def main():
     print(json.dumps(line), flush=True)
     if n_gpus > 1:
         dist.destroy_process_group()
+    parity = extras.get("parity")
+    if parity and not (parity["equals_single_gpu"] and parity["rays_equal"]):
+        print("bench.py: PARITY FAILURE — the multi-GPU frame differs from the single-GPU frame", file=sys.stderr)
+        return 3
     return 0
 
 

@@ -13,7 +13,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1u
+#define RT_B200_ABI_VERSION 2u   /* 2: RtRenderStats and RtRenderOptions grew (fused passes, work stealing) */
 
 /* RtRenderOptions::flags */
 #define RT_OPT_FIXED_JITTER 0x1u  /* deterministic mode: sub-pixel offset (0.5,0.5), no jitter draws */
@@ -28,6 +28,7 @@ extern "C" {
                                       spatial groups of 8 with conservative bounding spheres; a ray tests only the
                                       groups it can touch.  Same pixels and ray counts, fewer sphere tests.
                                       Worlds with fewer than 64 spheres ignore it. */
+#define RT_OPT_RESOLVE_EACH_PASS 0x200u /* passes > 1: refresh the RGBA8 frame after every pass, not only the last */
 #define RT_OPT_FULL_FRAME_OUT 0x20u /* rt_render_device with shard_count > 1: device_pixels / device_accum are
                                        FULL width*height frames (e.g. another GPU's frame mapped through CUDA IPC
                                        or peer access); this shard's tiles are stored at their frame offsets */
@@ -53,7 +54,18 @@ typedef struct RtRenderStats {
   uint32_t filtered;    /* 1: the exact kernel put its conservative FMA filter in front of the sphere tests */
   uint32_t sample_items;/* 1: work items were single samples; a second kernel summed them in order */
   uint32_t culled;      /* 1: the CULL kernels ran (RT_OPT_GROUP_CULL) */
+  uint32_t passes_fused;/* progressive passes traced by ONE persistent launch (0 or 1: a plain frame) */
+  uint32_t stolen_slots;/* pixel slots this call's GPU(s) took from other GPUs' shards (work stealing) */
 } RtRenderStats;
+
+/* One shard's block for cross-GPU work stealing (rt_shard_block_bytes bytes of device memory owned by
+ * the GPU that renders shard `shard_index`; mapped into the other processes with rt_ipc_open, or plain
+ * peer access inside one process). */
+typedef struct RtPeerQueue {
+  void    *block;
+  uint32_t shard_index;
+  uint32_t reserved;
+} RtPeerQueue;
 
 /* common.rs:289-294 `Options`, extended.  Zero-initialise, then set struct_size. */
 typedef struct RtRenderOptions {
@@ -72,6 +84,14 @@ typedef struct RtRenderOptions {
                                   devices 0..n-1 (row tiles d, d+N, ...; tiles are stored straight into
                                   device 0's frame over NVLink).  0 -> environment RT_GPUS, else 1 */
   RtRenderStats *stats;        /* optional out */
+  /* --- ABI version 2 (callers built against version 1 pass a smaller struct_size; these then read as 0) --- */
+  uint32_t passes;             /* 0 or 1: one pass.  k > 1: samples_per_pixel is traced as k progressive passes of
+                                  samples_per_pixel/k, the float4 sums going through device memory in between —
+                                  all inside ONE persistent launch (no drain between passes).  The frame equals the
+                                  single-pass frame bit for bit (common.rs:338-340 adds the samples in order). */
+  uint32_t n_peer_queues;      /* rt_render_device, shard_count > 1, RT_OPT_FULL_FRAME_OUT: cross-GPU work stealing. */
+  const RtPeerQueue *peer_queues; /* The blocks of ALL shard_count shards (this shard's own included), in the order
+                                  in which the others are raided once this shard's own queue is empty. */
 } RtRenderOptions;
 
 /* Thread-local text of the last failure of any call in this library ("" if none). */
@@ -171,6 +191,10 @@ void                 rt_free_pixels(struct Rust_ColorU8 *pixels);
  * rt_copy_to_host enqueues the final D2H on `stream`.  Pointers are NULL / results non-zero on
  * failure (rt_last_error). */
 void *rt_device_alloc(size_t bytes);
+/* Shard blocks (work stealing + fused passes across GPUs): size for a width x height frame, and the one-time
+ * initialisation by the owner ("queue empty") before anybody may be given the block. */
+size_t rt_shard_block_bytes(size_t width, size_t height);
+int    rt_shard_block_init(void *block);
 void  rt_device_free(void *device_ptr);
 int   rt_ipc_export(const void *device_ptr, unsigned char handle_out[64]);
 void *rt_ipc_open(const unsigned char handle[64]);

@@ -129,6 +129,10 @@ def lib() -> C.CDLL:
     L.orc_ray_trace.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_void_p, C.c_size_t, C.c_size_t,
                                 C.POINTER(Options), C.c_int32, C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_uint64)]
+    L.orc_ray_trace_rows.restype = C.c_int
+    L.orc_ray_trace_rows.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_void_p, C.c_size_t, C.c_size_t,
+                                     C.c_size_t, C.c_size_t, C.POINTER(Options), C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.POINTER(C.c_uint64)]
     L.orc_write_image.restype = C.c_int
     L.orc_write_image.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_char_p]
     _lib = L
@@ -229,8 +233,11 @@ def move_camera_position(cam: Camera, x, y, z) -> Camera:
 def ray_trace(world: World, camera: Camera, width: int, height: int, spp: int, depth: int, *,
               rng_mode: int = RNG_PER_SAMPLE, seed: int = SEED_DEFAULT, fixed_jitter: bool = False,
               sample_begin: int = 0, threads: int | None = None, resolve_spp: int | None = None,
-              accum_in: np.ndarray | None = None, want_accum: bool = False):
-    """common.rs:320-361.  Returns (pixels[H,W,4] uint8, ray_count, accum or None)."""
+              accum_in: np.ndarray | None = None, want_accum: bool = False,
+              rows: tuple[int, int] | None = None):
+    """common.rs:320-361.  Returns (pixels[H,W,4] uint8, ray_count, accum or None).
+    rows=(begin, end): only image rows [begin, end) (0 = top) are traced (per-sample RNG mode); the
+    rest of the returned frame stays zero and ray_count is the band's."""
     L = lib()
     if threads is None:
         threads = os.cpu_count() or 1
@@ -242,10 +249,15 @@ def ray_trace(world: World, camera: Camera, width: int, height: int, spp: int, d
         accum_in = np.ascontiguousarray(accum_in, dtype=np.float32)
         assert accum_in.shape == (height, width, 4)
     rays = C.c_uint64(0)
-    rc = L.orc_ray_trace(world.ptr, C.byref(camera), pixels.ctypes.data, width, height,
-                         C.byref(opt), int(resolve_spp if resolve_spp is not None else spp),
-                         accum_in.ctypes.data if accum_in is not None else None,
-                         accum.ctypes.data if accum is not None else None, C.byref(rays))
+    tail = (C.byref(opt), int(resolve_spp if resolve_spp is not None else spp),
+            accum_in.ctypes.data if accum_in is not None else None,
+            accum.ctypes.data if accum is not None else None, C.byref(rays))
+    if rows is not None:
+        assert rng_mode == RNG_PER_SAMPLE, "a row band is only defined for the per-sample RNG mode"
+        rc = L.orc_ray_trace_rows(world.ptr, C.byref(camera), pixels.ctypes.data, width, height,
+                                  int(rows[0]), int(rows[1]), *tail)
+    else:
+        rc = L.orc_ray_trace(world.ptr, C.byref(camera), pixels.ctypes.data, width, height, *tail)
     if rc:
         raise RuntimeError("orc_ray_trace failed: %d" % rc)
     return pixels, rays.value, accum

@@ -557,6 +557,36 @@ static void trace_pixel(const orc_world *w, const orc_camera *cam, size_t width,
     pixels[4 * out_index + 3] = orc_f32_as_u8(col.a * k * 255.999f);
 }
 
+/* common.rs:320-361 restricted to the image rows [image_row_begin, image_row_end) of the frame
+ * (image row 0 = top; the reference's loop row is height-1-image_row, :351).  Only meaningful in
+ * PER_SAMPLE mode, where every (pixel, sample) has its own stream and a band is therefore exactly
+ * the band of the full frame.  Pixels / accumulators outside the band are left untouched. */
+int orc_ray_trace_rows(const orc_world *w, const orc_camera *camera, uint8_t *pixels, size_t width,
+                       size_t height, size_t image_row_begin, size_t image_row_end,
+                       const orc_options *opt, int32_t resolve_spp,
+                       const float *accum_in, float *accum_out, uint64_t *ray_count_out)
+{
+    uint64_t total = 0;
+    if (opt->rng_mode != ORC_RNG_PER_SAMPLE) return 1;
+    if (image_row_end > height) image_row_end = height;
+    if (image_row_begin > image_row_end) image_row_begin = image_row_end;
+    int threads = opt->threads > 1 ? opt->threads : 1;
+    (void)threads;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads) reduction(+ : total)
+#endif
+    for (long ir = (long)image_row_begin; ir < (long)image_row_end; ++ir) {
+        uint64_t segs = 0;
+        size_t   row  = height - 1 - (size_t)ir;
+        for (size_t column = 0; column < width; ++column)
+            trace_pixel(w, camera, width, height, row, column, opt, resolve_spp, NULL,
+                        accum_in, accum_out, pixels, &segs);
+        total += segs;
+    }
+    if (ray_count_out) *ray_count_out = total;
+    return 0;
+}
+
 /* common.rs:320-361 */
 int orc_ray_trace(const orc_world *w, const orc_camera *camera, uint8_t *pixels, size_t width,
                   size_t height, const orc_options *opt, int32_t resolve_spp,

@@ -119,6 +119,16 @@ int orc_ray_trace(const orc_world *w, const orc_camera *camera,
                   const orc_options *opt, int32_t resolve_spp,
                   const float *accum_in, float *accum_out, uint64_t *ray_count_out);
 
+/* The same loop restricted to image rows [image_row_begin, image_row_end) (0 = top row), PER_SAMPLE
+ * mode only: with one stream per (pixel, sample) a band is exactly that band of the full frame, which
+ * is how full-width slices of the large BASELINE configs are checked in seconds.  Pixels and
+ * accumulators outside the band are not touched; ray_count_out counts the band's segments. */
+int orc_ray_trace_rows(const orc_world *w, const orc_camera *camera,
+                       uint8_t *pixels, size_t width, size_t height,
+                       size_t image_row_begin, size_t image_row_end,
+                       const orc_options *opt, int32_t resolve_spp,
+                       const float *accum_in, float *accum_out, uint64_t *ray_count_out);
+
 /* image.rs:59-81 — ASCII PPM (P3).  Returns 0 on success. */
 int orc_write_image(const uint8_t *pixels, size_t width, size_t height, const char *path);
 

@@ -40,6 +40,7 @@ OPT_FULL_FRAME_OUT = 0x20
 OPT_PIXEL_ITEMS = 0x40
 OPT_SAMPLE_ITEMS = 0x80
 OPT_GROUP_CULL = 0x100
+OPT_RESOLVE_EACH_PASS = 0x200
 DIFFUSE, METAL, DIELECTRIC, EMISSION = 0, 1, 2, 3   # materials.rs:7-12
 
 
@@ -68,10 +69,16 @@ class RenderStats(C.Structure):
                 ("total_ms", C.c_float), ("launches", C.c_uint32), ("grid", C.c_uint32),
                 ("smem_bytes", C.c_uint32), ("resident", C.c_uint32), ("block", C.c_uint32),
                 ("devices", C.c_uint32), ("peer_gather", C.c_uint32), ("filtered", C.c_uint32),
-                ("sample_items", C.c_uint32), ("culled", C.c_uint32)]
+                ("sample_items", C.c_uint32), ("culled", C.c_uint32),
+                ("passes_fused", C.c_uint32), ("stolen_slots", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class PeerQueue(C.Structure):
+    """RtPeerQueue: one shard's block (rt_shard_block_bytes) for cross-GPU work stealing."""
+    _fields_ = [("block", C.c_void_p), ("shard_index", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class _RenderOptions(C.Structure):
@@ -79,7 +86,8 @@ class _RenderOptions(C.Structure):
                 ("max_ray_bounces", C.c_int32), ("seed", C.c_uint32), ("flags", C.c_uint32),
                 ("sample_begin", C.c_int32), ("resolve_spp", C.c_int32), ("device", C.c_int32),
                 ("tile_rows", C.c_uint32), ("shard_index", C.c_uint32), ("shard_count", C.c_uint32),
-                ("n_devices", C.c_uint32), ("stats", C.POINTER(RenderStats))]
+                ("n_devices", C.c_uint32), ("stats", C.POINTER(RenderStats)),
+                ("passes", C.c_uint32), ("n_peer_queues", C.c_uint32), ("peer_queues", C.POINTER(PeerQueue))]
 
 
 _lib: Optional[C.CDLL] = None
@@ -95,7 +103,7 @@ EXPORTED_SYMBOLS = (
     "rt_world_sphere_count", "rt_world_triangle_count", "rt_world_get_sphere", "rt_world_get_triangle",
     "rt_world_to_text", "rt_write_image", "rt_write_image_p6",
     "rt_alloc_pixels", "rt_free_pixels", "rt_measure_fp32_peak", "rt_selftest_division",
-    "rt_device_alloc", "rt_device_free", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_copy_to_host",
+    "rt_device_alloc", "rt_device_free", "rt_shard_block_bytes", "rt_shard_block_init", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_copy_to_host",
 )
 
 
@@ -178,6 +186,10 @@ def lib() -> C.CDLL:
     L.rt_device_alloc.argtypes = [C.c_size_t]
     L.rt_device_free.restype = None
     L.rt_device_free.argtypes = [C.c_void_p]
+    L.rt_shard_block_bytes.restype = C.c_size_t
+    L.rt_shard_block_bytes.argtypes = [C.c_size_t, C.c_size_t]
+    L.rt_shard_block_init.restype = C.c_int
+    L.rt_shard_block_init.argtypes = [C.c_void_p]
     L.rt_ipc_export.restype = C.c_int
     L.rt_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
     L.rt_ipc_open.restype = C.c_void_p
@@ -225,17 +237,26 @@ class Options:
     n_devices: int = 0                   # > 1: this process renders on devices 0..n-1 (render_with_options only)
     sample_items: Optional[bool] = None  # scheduling: None auto, False whole pixels per lane, True single samples
     group_cull: bool = False             # opt-in acceleration: bounding spheres over groups of 8 spheres (same hits)
+    passes: int = 1                      # progressive passes of samples_per_pixel/passes, fused into one launch
+    resolve_each_pass: bool = False      # fused passes: refresh the RGBA8 frame after every pass
+    peer_queues: Optional[list] = None   # [(block address, shard index), ...] of ALL shards: cross-GPU work stealing
 
     def _c(self, stats: Optional[RenderStats]) -> _RenderOptions:
         flags = ((OPT_FIXED_JITTER if self.fixed_jitter else 0) | (OPT_FAST_MATH if self.fast_math else 0) |
                  (OPT_ACCUM_IN if self.accum_in else 0) | (OPT_ACCUM_OUT if self.accum_out else 0) |
                  (OPT_NO_RESOLVE if self.no_resolve else 0) | (OPT_FULL_FRAME_OUT if self.full_frame_out else 0) | (OPT_GROUP_CULL if self.group_cull else 0) |
+                 (OPT_RESOLVE_EACH_PASS if self.resolve_each_pass else 0) |
                  (0 if self.sample_items is None else OPT_SAMPLE_ITEMS if self.sample_items else OPT_PIXEL_ITEMS))
         o = _RenderOptions(C.sizeof(_RenderOptions), int(self.samples_per_pixel), int(self.max_ray_bounces),
                            int(self.seed) & 0xFFFFFFFF, flags, int(self.sample_begin), int(self.resolve_spp),
                            int(self.device), int(self.tile_rows), int(self.shard_index), int(self.shard_count),
                            int(self.n_devices),
-                           C.pointer(stats) if stats is not None else None)
+                           C.pointer(stats) if stats is not None else None, int(self.passes), 0, None)
+        if self.peer_queues:
+            arr = (PeerQueue * len(self.peer_queues))(*[PeerQueue(int(b), int(i), 0) for b, i in self.peer_queues])
+            o._keep = arr                     # the array must outlive the call
+            o.peer_queues = C.cast(arr, C.POINTER(PeerQueue))
+            o.n_peer_queues = len(self.peer_queues)
         return o
 
 
@@ -464,6 +485,15 @@ def device_alloc(nbytes: int) -> int:
 
 def device_free(ptr: int) -> None:
     lib().rt_device_free(C.c_void_p(ptr))
+
+
+def shard_block_bytes(width: int, height: int) -> int:
+    return lib().rt_shard_block_bytes(int(width), int(height))
+
+
+def shard_block_init(ptr: int) -> None:
+    if lib().rt_shard_block_init(C.c_void_p(ptr)):
+        raise RenderError(last_error())
 
 
 def ipc_export(ptr: int) -> bytes:

@@ -3,6 +3,7 @@
 #include "../../include/raytracer_b200.h"
 #include "rt_host.hpp"
 
+#include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <exception>
@@ -71,15 +72,27 @@ rt::Options to_options(const RtRenderOptions* o)
     r.tile_rows         = c.tile_rows ? c.tile_rows : 16u;
     r.shard_index       = c.shard_index;
     r.shard_count       = c.shard_count ? c.shard_count : 1u;
+    r.passes            = c.passes > 1u ? (int32_t)c.passes : 1;
+    r.resolve_each_pass = (c.flags & RT_OPT_RESOLVE_EACH_PASS) != 0;
+    static_assert(sizeof(RtPeerQueue) == sizeof(rt::PeerQueue), "RtPeerQueue mirrors rt::PeerQueue");
+    r.peer_queues       = reinterpret_cast<const rt::PeerQueue*>(c.peer_queues);
+    r.n_peer_queues     = c.peer_queues ? c.n_peer_queues : 0u;
     return r;
 }
 
-void export_stats(const rt::RenderStats& s, RtRenderStats* out)
+// A caller built against ABI version 1 passes the shorter RtRenderOptions and owns the shorter RtRenderStats:
+// only the version-1 fields are written for it.
+constexpr size_t kOptionsV1 = offsetof(RtRenderOptions, stats) + sizeof(RtRenderStats*);
+RtRenderStats* stats_of(const RtRenderOptions* o) { return (o && o->struct_size >= kOptionsV1) ? o->stats : nullptr; }
+bool           is_v2(const RtRenderOptions* o) { return o && o->struct_size >= sizeof(RtRenderOptions); }
+
+void export_stats(const rt::RenderStats& s, RtRenderStats* out, bool v2)
 {
     out->rays = s.rays; out->samples = s.samples; out->kernel_ms = s.kernel_ms; out->total_ms = s.total_ms;
     out->launches = s.launches; out->grid = s.grid; out->smem_bytes = s.smem_bytes; out->resident = s.resident;
     out->block = s.block; out->devices = s.devices; out->peer_gather = s.peer_gather; out->filtered = s.filtered;
     out->sample_items = s.sample_items; out->culled = s.culled;
+    if (v2) { out->passes_fused = s.passes_fused; out->stolen_slots = s.stolen_slots; }
 }
 
 template <class F>
@@ -158,7 +171,7 @@ Rust_CFramebuffer render_with_options(Rust_CFramebuffer fb, const Rust_WorldHand
         if (!fb.pixels) throw std::runtime_error("render: framebuffer.pixels is NULL");
         rt::Options     o = to_options(options);
         rt::RenderStats st;
-        RtRenderStats*  out_stats = (options && options->struct_size >= sizeof(RtRenderOptions)) ? options->stats : nullptr;
+        RtRenderStats*  out_stats = stats_of(options);
         if (out_stats) o.stats = &st;
         const int n_dev = o.n_devices > 0 ? o.n_devices : env_devices();
         if (n_dev > 1 && o.shard_count <= 1)
@@ -170,7 +183,7 @@ Rust_CFramebuffer render_with_options(Rust_CFramebuffer fb, const Rust_WorldHand
         else
             rt::ray_trace_into(*handle->world->world, handle->camera->camera, fb.width, fb.height, o,
                                reinterpret_cast<rt::ColorU8*>(fb.pixels), nullptr, nullptr, nullptr);
-        if (out_stats) export_stats(st, out_stats);
+        if (out_stats) export_stats(st, out_stats, is_v2(options));
     });
     return fb;
 }
@@ -201,14 +214,14 @@ Rust_CFramebuffer rt_render_progressive(Rust_CFramebuffer fb, const Rust_WorldHa
             if (p.cap_px < px || p.device != o.device) {
                 if (p.d_accum) rt::device_free(p.d_accum);
                 p.d_accum = nullptr; p.cap_px = 0;
-                p.d_accum = rt::device_alloc(px * 4 * sizeof(float));
+                p.d_accum = rt::device_alloc(px * 4 * sizeof(float), o.device);   // on the device that renders
                 p.cap_px  = px;
             }
             p.width = fb.width; p.height = fb.height; p.seed = o.seed; p.depth = o.max_ray_bounces;
             p.flags = key_flags; p.device = o.device; p.camera = handle->camera->camera; p.done = 0;
         }
         rt::RenderStats st;
-        RtRenderStats*  out_stats = (options && options->struct_size >= sizeof(RtRenderOptions)) ? options->stats : nullptr;
+        RtRenderStats*  out_stats = stats_of(options);
         if (out_stats) o.stats = &st;
         o.sample_begin = p.done;
         o.resolve_spp  = p.done + o.samples_per_pixel;
@@ -219,7 +232,7 @@ Rust_CFramebuffer rt_render_progressive(Rust_CFramebuffer fb, const Rust_WorldHa
                            reinterpret_cast<rt::ColorU8*>(fb.pixels), nullptr, p.d_accum, nullptr);
         p.done += o.samples_per_pixel;
         if (total_spp_out) *total_spp_out = p.done;
-        if (out_stats) export_stats(st, out_stats);
+        if (out_stats) export_stats(st, out_stats, is_v2(options));
     });
     return fb;
 }
@@ -241,12 +254,12 @@ int rt_render_device(const Rust_WorldHandle* handle, const RtRenderOptions* opti
         if (!handle || !handle->world || !handle->camera) throw std::runtime_error("rt_render_device: NULL world handle");
         rt::Options     o = to_options(options);
         rt::RenderStats st;
-        RtRenderStats*  out_stats = (options && options->struct_size >= sizeof(RtRenderOptions)) ? options->stats : nullptr;
+        RtRenderStats*  out_stats = stats_of(options);
         if (out_stats) o.stats = &st;
         if (!device_pixels && !o.no_resolve) throw std::runtime_error("rt_render_device: device_pixels is NULL");
         rt::ray_trace_into(*handle->world->world, handle->camera->camera, width, height, o, nullptr, device_pixels,
                            device_accum, stream);
-        if (out_stats) export_stats(st, out_stats);
+        if (out_stats) export_stats(st, out_stats, is_v2(options));
     });
 }
 
@@ -409,6 +422,8 @@ void* rt_device_alloc(size_t bytes)
     return p;
 }
 void rt_device_free(void* p) { rt::device_free(p); }
+size_t rt_shard_block_bytes(size_t width, size_t height) { return rt::shard_block_bytes(width, height); }
+int    rt_shard_block_init(void* block) { return guarded([&] { rt::shard_block_init(block); }); }
 int  rt_ipc_export(const void* device_ptr, unsigned char handle_out[64])
 {
     return guarded([&] { rt::ipc_export(device_ptr, handle_out); });

@@ -49,8 +49,14 @@ constexpr uint64_t kSampleBufferCap = (uint64_t)1 << 30;
 struct CounterSlot {            // 16 B, zeroed by one memset per launch
     unsigned long long rays;
     unsigned int       work;
-    unsigned int       pad;
+    unsigned int       stolen;
 };
+
+// Shard block (cross-GPU work stealing): the shard's work counter, alone in its first 256 bytes, then
+// the float4 sums of the fused passes for the full frame.  Lives in its owner's device memory; the
+// other GPUs reach it through peer access or a CUDA-IPC mapping.
+constexpr size_t       kBlockHeader    = 256;
+constexpr unsigned int kQueueExhausted = 0xC0000000u;   // any value >= every queue length (< 2^31)
 
 struct DeviceContext {
     int          device   = -1;
@@ -64,9 +70,10 @@ struct DeviceContext {
     uint32_t*    d_out    = nullptr;   size_t d_out_cap = 0;     // internal frame buffer (pixels)
     unsigned char* h_stage = nullptr;  size_t h_stage_cap = 0;   // pinned staging for pageable destinations
     RtFloat4*    d_samples = nullptr;  size_t d_samples_cap = 0; // per-sample colours of the sample-item mode
-    RtFloat4*    d_accum = nullptr;    size_t d_accum_cap = 0;   // hand-over sums between sample-item chunks
+    RtFloat4*    d_accum = nullptr;    size_t d_accum_cap = 0;   // hand-over sums between sample-item chunks / fused passes
+    unsigned char* d_block = nullptr;  size_t d_block_cap = 0;   // this device's shard block (ray_trace_multi)
     struct Geometry { int per_sm = 0, block = 0, resident = 0, sph_mode = 0; size_t hot_bytes = 0; };
-    std::map<std::tuple<uint32_t, uint32_t, int, int>, Geometry> occupancy;   // (Sp, Tp, fast, cull) -> launch geometry
+    std::map<std::tuple<uint32_t, uint32_t, uint32_t, int, int>, Geometry> occupancy;   // (Sp, Tp, groups, fast, cull) -> launch geometry
 };
 
 std::mutex                    g_mutex;          // one render at a time per process (lib.rs is single-threaded)
@@ -92,6 +99,19 @@ DeviceContext& context_for(int device)
     g_contexts[device] = c;
     return *c;
 }
+
+// Makes `device` current and restores the caller's current device when the scope ends.
+struct DeviceGuard {
+    int previous = -1;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&previous) != cudaSuccess) { cudaGetLastError(); previous = -1; }
+        RT_CUDA(cudaSetDevice(device));
+    }
+    ~DeviceGuard() { if (previous >= 0) cudaSetDevice(previous); }
+    DeviceGuard(const DeviceGuard&)            = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 int resolve_device(int requested)
 {
@@ -186,7 +206,7 @@ struct ShardLaunch {
     int          grid = 0, block = 0;
     size_t       hot_bytes = 0, smem_limit = 0;
     bool         resident = false, filtered = false, culled = false, sample_items = false;
-    uint32_t     launches = 0;
+    uint32_t     launches = 0, passes_fused = 0;
     CounterSlot* slot = nullptr;
     uint32_t*    d_out = nullptr;
 };
@@ -197,7 +217,17 @@ void validate(size_t width, size_t height, const Options& opt, const void* devic
     if (width > 0x3fffffffu || height > 0x3fffffffu) throw std::runtime_error("framebuffer too large");
     if (opt.tile_rows < 4 || (opt.tile_rows & 3u)) throw std::runtime_error("tile_rows must be a positive multiple of 4");
     if (opt.shard_count < 1 || opt.shard_index >= opt.shard_count) throw std::runtime_error("bad shard index/count");
-    if ((opt.accum_in || opt.accum_out) && !device_accum) throw std::runtime_error("accumulator requested but device_accum is null");
+    if ((opt.accum_in || opt.accum_out) && !device_accum && !opt.n_peer_queues)
+        throw std::runtime_error("accumulator requested but device_accum is null");
+    if (opt.passes > 1 && (opt.samples_per_pixel % opt.passes) != 0)
+        throw std::runtime_error("samples_per_pixel must be a multiple of passes");
+    if (opt.n_peer_queues) {
+        if (opt.n_peer_queues > RT_MAX_QUEUES) throw std::runtime_error("too many peer queues");
+        if (opt.n_peer_queues != opt.shard_count) throw std::runtime_error("peer_queues must list every shard of the frame");
+        if (!opt.full_frame_out) throw std::runtime_error("work stealing needs a full-frame destination (RT_OPT_FULL_FRAME_OUT)");
+        if (opt.accum_in || opt.accum_out || opt.no_resolve || device_accum)
+            throw std::runtime_error("work stealing keeps its sums in the shard blocks: no caller accumulator");
+    }
 }
 
 ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Camera& camera, uint32_t W, uint32_t H,
@@ -206,7 +236,6 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     ShardLaunch L;
     L.n_tiles = shard_tile_count(H, opt.tile_rows, opt.shard_index, opt.shard_count);
     const uint64_t slots = (uint64_t)L.n_tiles * ((W + 7u) / 8u) * (opt.tile_rows / 4u) * 32u;
-    if (slots >= 0xffffff00ull) throw std::runtime_error("frame shard exceeds 2^32 pixel slots; use more shards");
     L.compact    = opt.shard_count > 1 && !opt.full_frame_out;
     L.out_pixels = L.compact ? (size_t)L.n_tiles * opt.tile_rows * W : (size_t)W * H;
 
@@ -221,6 +250,8 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
         L.d_out = ctx.d_out;
     }
     L.slot = ctx.d_slots + (ctx.next_slot++ % kCounterSlots);
+
+    const bool trace = opt.samples_per_pixel > 0 && opt.max_ray_bounces > 0;
 
     RtFrameParams P{};
     P.camera       = camera.d;
@@ -240,10 +271,12 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     P.tile_first   = opt.shard_index;
     P.tile_stride  = opt.shard_count;
     P.n_tiles      = L.n_tiles;
+    P.passes       = 1;
     P.out          = L.d_out;
     P.accum        = static_cast<RtFloat4*>(device_accum);
     P.ray_counter  = &L.slot->rays;
     P.work_counter = &L.slot->work;
+    P.steal_counter = &L.slot->stolen;
 
     // Work-item granularity.  A lane normally owns a whole pixel (all its samples, summed in
     // order in registers).  When the frame offers only a few pixels per lane and every ray
@@ -260,13 +293,13 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
         const bool     want = opt.sample_items > 0 ||
                               (opt.sample_items < 0 && prims >= 512 && opt.samples_per_pixel >= 4 &&
                                pixels < 16u * lanes_max);
-        L.sample_items = want && opt.samples_per_pixel > 0 && opt.max_ray_bounces > 0 && L.n_tiles > 0;
+        L.sample_items = want && trace && L.n_tiles > 0;
         if (L.sample_items) {
             // the sample buffer is capped (1 GiB): more samples than fit are traced in several
             // launches that hand their sums on through the float4 accumulator
             const uint64_t per_sample = L.out_pixels * sizeof(RtFloat4);
             const uint64_t cap_spp    = std::max<uint64_t>(kSampleBufferCap / std::max<uint64_t>(per_sample, 1), 1);
-            const uint64_t slot_spp   = std::max<uint64_t>(0xffffff00ull / std::max<uint64_t>(slots, 1), 1) - 0;
+            const uint64_t slot_spp   = std::max<uint64_t>(0x7fffff00ull / std::max<uint64_t>(slots, 1), 1) - 0;
             chunk_spp = (int32_t)std::min<uint64_t>({(uint64_t)opt.samples_per_pixel, cap_spp, slot_spp});
             const uint64_t buf_bytes = per_sample * (uint64_t)chunk_spp;
             if (ctx.d_samples_cap < buf_bytes) {
@@ -293,9 +326,60 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
         }
     }
 
+    // Cross-GPU work stealing: the queue table of this launch, own shard first.
+    const bool     stealing  = opt.n_peer_queues > 1 && !L.sample_items && trace;
+    unsigned char* own_block = nullptr;
+    for (uint32_t i = 0; i < opt.n_peer_queues; ++i)
+        if (opt.peer_queues[i].shard_index == opt.shard_index) own_block = static_cast<unsigned char*>(opt.peer_queues[i].block);
+    if (opt.n_peer_queues && !own_block) throw std::runtime_error("peer_queues does not contain this shard's own block");
+    if (own_block && !L.sample_items) P.accum = reinterpret_cast<RtFloat4*>(own_block + kBlockHeader);
+    if (stealing) {
+        P.work_counter = reinterpret_cast<unsigned int*>(own_block);
+        uint32_t n = 0;
+        P.queues[n++] = RtQueue{P.work_counter, P.accum, opt.shard_index, L.n_tiles};
+        for (uint32_t i = 0; i < opt.n_peer_queues; ++i) {
+            const PeerQueue& pq = opt.peer_queues[i];
+            if (pq.shard_index == opt.shard_index) continue;
+            if (pq.shard_index >= opt.shard_count || !pq.block) throw std::runtime_error("bad peer queue entry");
+            unsigned char* b = static_cast<unsigned char*>(pq.block);
+            P.queues[n++] = RtQueue{reinterpret_cast<unsigned int*>(b), reinterpret_cast<RtFloat4*>(b + kBlockHeader),
+                                    pq.shard_index, shard_tile_count(H, opt.tile_rows, pq.shard_index, opt.shard_count)};
+        }
+        P.n_queues = n;
+    }
+
+    // Progressive passes fused into this launch (rt_types.h): needs a fresh frame (the alpha sum tags the
+    // pass) and whole-pixel items; otherwise the total is traced as one pass — the same bits either way.
+    const bool fused = opt.passes > 1 && trace && !L.sample_items && !opt.accum_in &&
+                       (uint64_t)opt.sample_begin + (uint64_t)opt.samples_per_pixel < (1u << 24);
+    if (fused) {
+        P.passes = (uint32_t)opt.passes;
+        P.spp    = opt.samples_per_pixel / opt.passes;
+        if (opt.resolve_each_pass) P.flags |= RT_FLAG_RESOLVE_EACH_PASS;
+        if (!P.accum) {
+            const size_t need = L.out_pixels * sizeof(RtFloat4);
+            if (ctx.d_accum_cap < need) {
+                RT_CUDA(cudaStreamSynchronize(stream));
+                if (ctx.d_accum) RT_CUDA(cudaFree(ctx.d_accum));
+                ctx.d_accum = nullptr; ctx.d_accum_cap = 0;
+                RT_CUDA(cudaMalloc(&ctx.d_accum, need));
+                ctx.d_accum_cap = need;
+            }
+            P.accum = ctx.d_accum;
+        }
+        if (stealing) P.queues[0].accum = P.accum;
+        L.passes_fused = P.passes;
+    }
+    if (!stealing) {                                   // the launch's only queue: its own shard
+        P.n_queues  = 1;
+        P.queues[0] = RtQueue{P.work_counter, P.accum, opt.shard_index, L.n_tiles};
+    }
+    if ((uint64_t)slots * P.passes >= 0x7fffff00ull) throw std::runtime_error("frame shard exceeds 2^31 work slots; use more shards or fewer passes");
+
     // launch geometry: persistent CTAs, resident-CTA count from the occupancy API
     L.smem_limit = ctx.smem_optin > 1024 ? ctx.smem_optin - 1024 : 0;   // static smem: the mbarrier
-    auto& occ    = ctx.occupancy[{scene.view.n_sph_pad, scene.view.n_tri_pad, opt.fast_math ? 1 : 0, opt.group_cull ? 1 : 0}];
+    auto& occ    = ctx.occupancy[{scene.view.n_sph_pad, scene.view.n_tri_pad, scene.view.n_groups, opt.fast_math ? 1 : 0,
+                                  opt.group_cull ? 1 : 0}];
     if (occ.per_sm == 0) {
         RT_CUDA(opt.fast_math ? occupancy_fast(scene.view, L.smem_limit, opt.group_cull, &occ.per_sm, &occ.block,
                                                &occ.hot_bytes, &occ.resident, &occ.sph_mode)
@@ -308,8 +392,15 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     L.filtered  = occ.sph_mode != RT_SPH_DIRECT;
     L.culled    = occ.sph_mode == RT_SPH_CULL;
     L.block = occ.block;
-    const uint64_t work_slots = L.sample_items ? slots * (uint64_t)chunk_spp : slots;
-    const uint64_t want_ctas = (work_slots + (uint64_t)L.block - 1) / (uint64_t)L.block;
+    // with stealing every GPU may end up tracing any part of the frame: size the grid for the whole frame
+    uint64_t frame_slots = slots;
+    if (stealing) {
+        frame_slots = 0;
+        for (uint32_t i = 0; i < P.n_queues; ++i)
+            frame_slots += (uint64_t)P.queues[i].n_tiles * ((W + 7u) / 8u) * (opt.tile_rows / 4u) * 32u;
+    }
+    const uint64_t work_slots = L.sample_items ? slots * (uint64_t)chunk_spp : slots * P.passes;
+    const uint64_t want_ctas = ((stealing ? frame_slots * P.passes : work_slots) + (uint64_t)L.block - 1) / (uint64_t)L.block;
     L.grid = (int)std::min<uint64_t>((uint64_t)occ.per_sm * ctx.num_sms, std::max<uint64_t>(want_ctas, 1));
     // Work-queue granularity: a warp takes `reserve` pixel slots per atomicAdd.  Aim for >= 64
     // slabs per warp so that the last slab of the slowest warp is a small part of the frame.
@@ -317,8 +408,12 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     uint64_t       reserve = work_slots / (warps * 64u) / 32u * 32u;
     P.reserve = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(reserve, 32u), 256u);
 
-    if (L.n_tiles > 0) {
+    if (L.n_tiles > 0 || stealing) {
         RT_CUDA(cudaMemsetAsync(L.slot, 0, sizeof(CounterSlot), stream));
+        // fused passes: no stale sums may look like a finished pass.  Stream order puts this BEFORE the reset
+        // of the work counter, so no other GPU can be handed a slot of this shard while its sums are cleared.
+        if (fused) RT_CUDA(cudaMemsetAsync(P.accum, 0, L.out_pixels * sizeof(RtFloat4), stream));
+        if (stealing) RT_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), stream));
         if (timed) RT_CUDA(cudaEventRecord(ctx.ev0, stream));
         if (!L.sample_items) {
             RT_CUDA(opt.fast_math ? launch_render_fast(P, scene.view, L.grid, L.smem_limit, stream)
@@ -379,8 +474,8 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
     std::lock_guard<std::mutex> lock(g_mutex);
     validate(width, height, opt, device_accum);
 
-    const int dev = resolve_device(opt.device);
-    RT_CUDA(cudaSetDevice(dev));
+    const int   dev = resolve_device(opt.device);
+    DeviceGuard guard(dev);                  // the caller's current device is restored on every exit path
     DeviceContext&     ctx   = context_for(dev);
     const DeviceScene& scene = device_scene(world, ctx);
     cudaStream_t       stream = user_stream ? static_cast<cudaStream_t>(user_stream) : ctx.stream;
@@ -393,8 +488,17 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
     // a 1-spp 1080p frame takes 1.27 ms this way against 0.37 ms with the copy), a D2H copy ~50 GB/s.
     const uint64_t work_per_pixel = (uint64_t)std::max(opt.samples_per_pixel, 0) *
                                     ((uint64_t)scene.view.n_sph + scene.view.n_tri + 8u);
-    void* zero_copy = (host_pixels && !device_pixels && !opt.no_resolve && work_per_pixel >= 256u)
-                          ? mapped_device_pointer(host_pixels) : nullptr;
+    const bool want_zero_copy = host_pixels && !device_pixels && !opt.no_resolve && work_per_pixel >= 256u;
+    void*      zero_copy      = want_zero_copy ? mapped_device_pointer(host_pixels) : nullptr;
+    // Pageable destination (what the reference's callers pass: UnsafeMutablePointer.allocate in
+    // GameView.swift:125-129, a Vec in examples/c_raytracer.rs:53): the kernel stores its pixels into the
+    // library's pinned staging frame the same way, and one memcpy hands them over — no D2H copy either.
+    bool staged_zero_copy = false;
+    if (want_zero_copy && !zero_copy && !is_pinned_or_device_accessible(host_pixels)) {
+        ensure_stage(ctx, (size_t)W * H * 4);
+        zero_copy = mapped_device_pointer(ctx.h_stage);
+        staged_zero_copy = zero_copy != nullptr;
+    }
     Options       zc_opt = opt;
     if (zero_copy) zc_opt.full_frame_out = true;            // tiles land at their frame offsets
     const ShardLaunch L = enqueue_shard(ctx, scene, camera, W, H, zero_copy ? zc_opt : opt,
@@ -405,6 +509,18 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
 
     if (zero_copy) {
         RT_CUDA(cudaStreamSynchronize(stream));
+        if (staged_zero_copy) {              // this shard's rows of the staging frame -> the caller's frame
+            const size_t tile_px = (size_t)opt.tile_rows * W;
+            if (opt.shard_count <= 1) {
+                std::memcpy(host_pixels, ctx.h_stage, (size_t)W * H * 4);
+            } else {
+                for (uint32_t j = 0; j < n_tiles; ++j) {
+                    const size_t first = (size_t)rt_shard_tile(opt.shard_index, opt.shard_count, j) * tile_px;
+                    const size_t count = std::min(tile_px, (size_t)W * H - first);
+                    std::memcpy(reinterpret_cast<unsigned char*>(host_pixels) + first * 4, ctx.h_stage + first * 4, count * 4);
+                }
+            }
+        }
     } else if (host_pixels && !opt.no_resolve && n_tiles > 0) {
         // D2H of the finished RGBA8 rows.  Every tile is one contiguous byte range of the frame
         // (image.rs:27 row-major), so a shard copies tile by tile and a full frame in one piece.
@@ -449,6 +565,8 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
             RT_CUDA(cudaStreamSynchronize(stream));
             RT_CUDA(cudaEventElapsedTime(&st.kernel_ms, ctx.ev0, ctx.ev1));
             st.rays     = ctx.h_slot->rays;
+            st.stolen_slots = ctx.h_slot->stolen;
+            st.passes_fused = L.passes_fused;
             st.launches = L.launches;
             st.sample_items = L.sample_items ? 1u : 0u;
             st.samples  = (opt.samples_per_pixel > 0 && opt.max_ray_bounces > 0)
@@ -481,34 +599,43 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
     if (N <= 1) {
         Options o = opt_in;
         o.device = 0; o.shard_index = 0; o.shard_count = 1; o.full_frame_out = false;
+        o.peer_queues = nullptr; o.n_peer_queues = 0;
         ray_trace_into(world, camera, width, height, o, host_pixels, nullptr, nullptr, nullptr);
         return;
     }
     std::unique_lock<std::mutex> lock(g_mutex);
+    int caller_device = -1;
+    if (cudaGetDevice(&caller_device) != cudaSuccess) { cudaGetLastError(); caller_device = -1; }
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{caller_device};
     Options base = opt_in;
     base.shard_count = (uint32_t)N;
+    base.peer_queues = nullptr; base.n_peer_queues = 0;
     validate(width, height, base, nullptr);
     const uint32_t W = (uint32_t)width, H = (uint32_t)height;
 
-    // contexts, scenes, peer access to device 0
+    // contexts, scenes, peer access: to device 0 for the fused gather, all-to-all for work stealing
     std::vector<DeviceContext*> ctxs(N);
-    bool peer = true;
+    bool peer = true, all_peer = N <= (int)RT_MAX_QUEUES;
     for (int d = 0; d < N; ++d) {
         RT_CUDA(cudaSetDevice(d));
         ctxs[d] = &context_for(d);
         (void)device_scene(world, *ctxs[d]);
-        if (d > 0) {
+        for (int e = 0; e < N; ++e) {
+            if (e == d) continue;
             int can = 0;
-            RT_CUDA(cudaDeviceCanAccessPeer(&can, d, 0));
+            RT_CUDA(cudaDeviceCanAccessPeer(&can, d, e));
             if (can) {
-                cudaError_t e = cudaDeviceEnablePeerAccess(0, 0);
-                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) fail("cudaDeviceEnablePeerAccess", e);
+                cudaError_t err = cudaDeviceEnablePeerAccess(e, 0);
+                if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled) fail("cudaDeviceEnablePeerAccess", err);
                 cudaGetLastError();
             } else {
-                peer = false;
+                all_peer = false;
+                if (e == 0) peer = false;
             }
         }
     }
+    static const bool steal_enabled = [] { const char* e = std::getenv("RT_STEAL"); return !(e && *e == '0'); }();
+    const bool steal = peer && all_peer && steal_enabled;
     DeviceContext& c0 = *ctxs[0];
     RT_CUDA(cudaSetDevice(0));
     if (c0.d_out_cap < (size_t)W * H) {
@@ -517,6 +644,24 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
         c0.d_out = nullptr; c0.d_out_cap = 0;
         RT_CUDA(cudaMalloc(&c0.d_out, (size_t)W * H * sizeof(uint32_t)));
         c0.d_out_cap = (size_t)W * H;
+    }
+    // shard blocks: every device's work counter (+ the sums of fused passes), reachable from all the others
+    std::vector<PeerQueue> blocks;
+    if (steal) {
+        const size_t need = base.passes > 1 ? shard_block_bytes(W, H) : kBlockHeader;
+        for (int d = 0; d < N; ++d) {
+            DeviceContext& c = *ctxs[d];
+            if (c.d_block_cap < need) {
+                RT_CUDA(cudaSetDevice(d));
+                RT_CUDA(cudaStreamSynchronize(c.stream));
+                if (c.d_block) RT_CUDA(cudaFree(c.d_block));
+                c.d_block = nullptr; c.d_block_cap = 0;
+                RT_CUDA(cudaMalloc(&c.d_block, need));
+                c.d_block_cap = need;
+                shard_block_init(c.d_block);
+            }
+        }
+        blocks.resize(N);
     }
 
     std::vector<ShardLaunch> launches(N);
@@ -527,6 +672,13 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
         RT_CUDA(cudaSetDevice(d));
         Options o = base;
         o.device = d; o.shard_index = (uint32_t)d; o.full_frame_out = peer;
+        if (steal) {                                   // raid order: the next device first, so that the thieves spread
+            for (int i = 0; i < N; ++i) {
+                const int e = (d + i) % N;
+                blocks[i] = PeerQueue{ctxs[e]->d_block, (uint32_t)e, 0u};
+            }
+            o.peer_queues = blocks.data(); o.n_peer_queues = (uint32_t)N;
+        }
         launches[d] = enqueue_shard(*ctxs[d], device_scene(world, *ctxs[d]), camera, W, H, o,
                                     peer ? c0.d_out : nullptr, nullptr, ctxs[d]->stream, true);
         if (!peer && launches[d].n_tiles > 0) {        // fallback gather: D2H tile by tile from every device
@@ -570,7 +722,7 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
         st.devices    = (uint32_t)N;
         st.peer_gather = peer ? 1u : 0u;
         for (int d = 0; d < N; ++d) {
-            if (launches[d].n_tiles == 0) continue;
+            if (launches[d].launches == 0) continue;
             RT_CUDA(cudaSetDevice(d));
             DeviceContext& c = *ctxs[d];
             RT_CUDA(cudaMemcpyAsync(c.h_slot, launches[d].slot, sizeof(CounterSlot), cudaMemcpyDeviceToHost, c.stream));
@@ -579,16 +731,16 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
             RT_CUDA(cudaEventElapsedTime(&ms, c.ev0, c.ev1));
             st.kernel_ms = std::max(st.kernel_ms, ms);          // devices run concurrently
             st.rays += c.h_slot->rays;
+            st.stolen_slots += c.h_slot->stolen;
+            st.passes_fused = launches[d].passes_fused;
             st.launches += launches[d].launches;
             st.sample_items = launches[d].sample_items ? 1u : 0u;
             Options o = base; o.shard_index = (uint32_t)d;
             if (base.samples_per_pixel > 0 && base.max_ray_bounces > 0)
                 st.samples += shard_pixels(W, H, o, launches[d].n_tiles) * (uint64_t)base.samples_per_pixel;
         }
-        RT_CUDA(cudaSetDevice(0));
         st.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     }
-    RT_CUDA(cudaSetDevice(0));
 }
 
 Framebuffer ray_trace(const World& world, const Camera& camera, Framebuffer framebuffer, Options& options)
@@ -659,13 +811,43 @@ long long selftest_division(int device, unsigned long long operand_sets, uint32_
 }
 
 // ---- device memory helpers for the multi-process peer-store gather (multi.py) ----
-void* device_alloc(size_t bytes)
+void* device_alloc(size_t bytes, int device)
 {
     void* p = nullptr;
+    if (device < 0) { RT_CUDA(cudaMalloc(&p, bytes)); return p; }
+    DeviceGuard guard(resolve_device(device));
     RT_CUDA(cudaMalloc(&p, bytes));
     return p;
 }
-void device_free(void* p) { if (p) cudaFree(p); }
+void device_free(void* p)
+{
+    if (!p) return;
+    cudaPointerAttributes a;
+    int cur = -1;
+    if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice &&
+        cudaGetDevice(&cur) == cudaSuccess && cur != a.device) {
+        cudaSetDevice(a.device);
+        cudaFree(p);
+        cudaSetDevice(cur);
+        return;
+    }
+    cudaGetLastError();
+    cudaFree(p);
+}
+
+size_t shard_block_bytes(size_t width, size_t height) { return kBlockHeader + width * height * sizeof(RtFloat4); }
+void   shard_block_init(void* block)
+{
+    if (!block) throw std::runtime_error("shard_block_init: null block");
+    cudaPointerAttributes a;
+    RT_CUDA(cudaPointerGetAttributes(&a, block));
+    if (a.type != cudaMemoryTypeDevice) throw std::runtime_error("shard_block_init: not device memory");
+    DeviceGuard guard(a.device);
+    // the whole header is set to the 'queue empty' value; the sums are cleared by every fused-pass frame itself
+    RT_CUDA(cudaMemset(block, 0, kBlockHeader));
+    const unsigned int v = kQueueExhausted;
+    RT_CUDA(cudaMemcpy(block, &v, sizeof v, cudaMemcpyHostToDevice));
+}
 void ipc_export(const void* device_ptr, unsigned char handle_out[64])
 {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");

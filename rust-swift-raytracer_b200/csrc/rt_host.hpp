@@ -78,6 +78,11 @@ struct Framebuffer {
 };
 
 // Per-render statistics (additive; the reference reports nothing).
+// One shard's block for cross-GPU work stealing: [work counter, 256 B][float4 sums, width*height].
+struct PeerQueue { void* block; uint32_t shard_index; uint32_t reserved; };
+size_t shard_block_bytes(size_t width, size_t height);
+void   shard_block_init(void* block);        // marks the queue empty (call once after allocating, on the owner)
+
 struct RenderStats {
     uint64_t rays       = 0;     // World::hit calls (ray segments)
     uint64_t samples    = 0;     // pixel samples traced
@@ -93,6 +98,8 @@ struct RenderStats {
     uint32_t filtered   = 0;     // 1: exact kernel ran its conservative sphere filter (large sphere lists)
     uint32_t sample_items = 0;   // 1: work items were single samples (ordered sum by the resolve kernel)
     uint32_t culled     = 0;     // 1: the CULL kernels ran (group bounds in front of the filter)
+    uint32_t passes_fused = 0;   // progressive passes traced by one persistent launch (0/1: a plain frame)
+    uint32_t stolen_slots = 0;   // pixel slots this GPU took from other GPUs' shards (cross-GPU work stealing)
 };
 
 // common.rs:289-294, extended.  The reference fields keep their names.
@@ -119,6 +126,17 @@ struct Options {
     int32_t  sample_items   = -1;           // work-item granularity: -1 auto, 0 whole pixels, 1 single samples
     bool     group_cull     = false;        // opt-in: skip whole groups of spheres through bounding spheres (same
                                             // hits; a separately reported mode — it changes the work done)
+    // Progressive passes: samples_per_pixel is traced as `passes` passes of samples_per_pixel/passes, the
+    // float4 sums going through device memory between passes (k x n spp == k*n spp bit for bit).  All
+    // passes run in ONE persistent launch (pass-major work queue, rt_types.h) unless the frame continues
+    // an accumulator (accum_in) or uses sample items, where a single pass of the total is traced instead.
+    int32_t  passes            = 1;
+    bool     resolve_each_pass = false;     // fused passes: the RGBA8 frame is refreshed after every pass
+    // Cross-GPU work stealing (shard_count > 1 with full_frame_out): the shard blocks (shard_block_bytes)
+    // of ALL shards of the frame, this shard's own among them, each in its owner's device memory and
+    // mapped here (peer access / CUDA IPC).  Order = the order in which the others are raided.
+    const PeerQueue* peer_queues   = nullptr;
+    uint32_t         n_peer_queues = 0;
     RenderStats* stats      = nullptr;
 };
 
@@ -201,7 +219,7 @@ double measure_fp32_peak_tflops(int device, float* sm_clock_mhz_out);
 long long selftest_division(int device, unsigned long long operand_sets, uint32_t seed);
 // Device memory that can be mapped into other processes (CUDA IPC): rank 0 owns the frame,
 // the other ranks' kernels store their tiles into it.  All throw std::runtime_error on failure.
-void* device_alloc(size_t bytes);
+void* device_alloc(size_t bytes, int device = -1);   // -1: the current device
 void  device_free(void* p);
 void  ipc_export(const void* device_ptr, unsigned char handle_out[64]);
 void* ipc_open(const unsigned char handle[64]);

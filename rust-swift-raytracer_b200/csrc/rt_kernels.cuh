@@ -93,8 +93,12 @@ struct PixelSlot {
 };
 
 __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_t slot, uint32_t subtiles_x,
-                                                 uint32_t chunks_per_strip, uint32_t& sample_of_item)
+                                                 uint32_t chunks_per_strip, uint32_t q_first, uint32_t q_tiles,
+                                                 uint32_t slots_per_pass, uint32_t& sample_of_item, uint32_t& pass)
 {
+    // Pass-major work space (fused progressive passes, rt_types.h): all of pass 0, then all of pass 1, ...
+    pass = 0u;
+    if (P.passes > 1u) { pass = slot / slots_per_pass; slot -= pass * slots_per_pass; }
     // Slots run from the BOTTOM of the frame upwards: rows near the ground carry the long
     // paths, rows of sky end after one segment, so the expensive pixels are handed out first
     // and the tail of the launch (when the queue is empty and lanes drain) is made of cheap
@@ -110,14 +114,14 @@ __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_
         chunk            = c;
     }
     const uint32_t rs    = chunk / chunks_per_strip;
-    const uint32_t strip = P.n_tiles - 1u - rs;
+    const uint32_t strip = q_tiles - 1u - rs;
     const uint32_t rc    = chunk - rs * chunks_per_strip;
     const uint32_t c     = chunks_per_strip - 1u - rc;
     const uint32_t sy    = c / subtiles_x;
     const uint32_t sx    = c - sy * subtiles_x;
     const uint32_t x     = sx * 8u + (in & 7u);
     const uint32_t yin   = sy * 4u + (in >> 3);
-    const uint32_t tile  = rt_shard_tile(P.tile_first, P.tile_stride, strip);
+    const uint32_t tile  = rt_shard_tile(q_first, P.tile_stride, strip);
     PixelSlot s;
     s.column    = x;
     s.image_row = tile * P.tile_rows + yin;
@@ -125,6 +129,23 @@ __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_
     const uint32_t out_row = (P.flags & RT_FLAG_COMPACT_OUT) ? strip * P.tile_rows + yin : s.image_row;
     s.out_index = out_row * P.width + x;
     return s;
+}
+
+// The float4 sums of a pixel between fused passes: ONE 16-byte access each way, at system scope
+// (SASS LDG/STG.E.128.STRONG.SYS), so that the record — colour sums plus the alpha channel that
+// counts the samples and thereby tags the pass — is seen whole by whichever SM or GPU traces the
+// pixel's next pass, without going through a (possibly stale) L1 line.
+__device__ __forceinline__ float4 accum_load(const RtFloat4* p)
+{
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void accum_store(RtFloat4* p, float4 v)
+{
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 #ifndef RT_MIN_CTAS_SMALL
@@ -176,17 +197,23 @@ __global__ void __launch_bounds__(BLOCK, BLOCK != 256 ? 1 : SPH != RT_SPH_DIRECT
     const uint32_t chunks_per_strip = subtiles_x * (P.tile_rows >> 2);
     const bool     trace            = (P.spp > 0) && (P.depth > 0);
     const bool     items            = (P.flags & RT_FLAG_SAMPLE_ITEMS) != 0;      // host sets it only when trace
-    const uint32_t total_slots      = P.n_tiles * chunks_per_strip * 32u * (items ? (uint32_t)P.spp : 1u);
+    const uint32_t slots_per_tile   = chunks_per_strip * 32u * (items ? (uint32_t)P.spp : 1u);
+    const uint32_t passes           = P.passes > 1u ? P.passes : 1u;
+
+    // The queue this warp draws from (P.queues[q]; q == P.n_queues: nothing left anywhere): its own shard
+    // first, then — multi-GPU — the other shards.  Everything else about a queue is re-read from the
+    // kernel parameters where it is needed (slab refill, slot decode), not carried in registers.
+    uint32_t q = 0u;
 
     // warp-uniform slab of reserved pixel slots
     uint32_t pool_next = 0, pool_end = 0;
-    bool     exhausted = false;
 
     Lane L;
     L.have = false;
     L.fcol = L.frow = 0.f;
     L.pix_hash = L.out_index = 0u;
     L.sample = 0; L.seg_left = 0; L.rng = 1u; L.pend_unit = false;
+    L.ctl = 0u;
     L.acc_r = L.acc_g = L.acc_b = 0.f;
     L.o = L.pend = L.thr = mk(0.f, 0.f, 0.f);
     uint32_t segments = 0;
@@ -194,28 +221,40 @@ __global__ void __launch_bounds__(BLOCK, BLOCK != 256 ? 1 : SPH != RT_SPH_DIRECT
     for (;;) {
         // ---- 1. lanes without a pixel take the next slots of the warp's slab ----
         uint32_t need = __ballot_sync(FULL, !L.have);
-        while (need && !exhausted) {
+        while (need && q < P.n_queues) {
             if (pool_next == pool_end) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(P.work_counter, P.reserve);
+                const uint32_t total = P.queues[q].n_tiles * slots_per_tile * passes;
+                uint32_t       base  = 0;
+                if (lane == 0)
+                    base = P.n_queues > 1u ? atomicAdd_system(P.queues[q].work_counter, P.reserve)
+                                           : atomicAdd(P.queues[q].work_counter, P.reserve);
                 base = __shfl_sync(FULL, base, 0);
-                if (base >= total_slots) { exhausted = true; break; }
+                if (base >= total) { ++q; continue; }      // this shard has no unassigned work left: raid the next one
                 pool_next = base;
-                pool_end  = min(base + P.reserve, total_slots);
+                pool_end  = min(base + P.reserve, total);
+                if (q && lane == 0 && P.steal_counter) atomicAdd(P.steal_counter, pool_end - pool_next);
             }
             const uint32_t avail = pool_end - pool_next;
             const uint32_t rank  = __popc(need & lt);
             if (!L.have && rank < avail) {
-                uint32_t  item_sample;
-                PixelSlot s = decode_slot(P, pool_next + rank, subtiles_x, chunks_per_strip, item_sample);
+                uint32_t  item_sample, pass;
+                const uint32_t q_tiles = P.queues[q].n_tiles;
+                PixelSlot s = decode_slot(P, pool_next + rank, subtiles_x, chunks_per_strip, P.queues[q].tile_first, q_tiles,
+                                          q_tiles * slots_per_tile, item_sample, pass);
                 if (s.valid) {
                     begin_pixel(L, P, s.column, P.height - 1u - s.image_row, s.out_index);   // common.rs:351 (flip)
+                    L.ctl = pass | (q << 16);
                     if (items) {                       // one sample: sums start at 0, colour goes to the sample buffer
                         L.sample    = (int32_t)item_sample;
                         L.out_index = item_sample * P.sample_stride + s.out_index;
-                    } else if (P.flags & RT_FLAG_ACCUM_IN) {
-                        RtFloat4 a = ld4(&P.accum[s.out_index]);
-                        L.acc_r = a.x; L.acc_g = a.y; L.acc_b = a.z;      // a.w is re-read at the end
+                    } else {
+                        L.sample = (int32_t)(pass * (uint32_t)P.spp);
+                        if (pass > 0u) {
+                            L.ctl |= RT_LANE_WAIT;     // starts from the sums of the pixel's previous pass (step 1b)
+                        } else if (P.flags & RT_FLAG_ACCUM_IN) {
+                            RtFloat4 a = ld4(&P.queues[0].accum[s.out_index]);
+                            L.acc_r = a.x; L.acc_g = a.y; L.acc_b = a.z;      // a.w is re-read at the end
+                        }
                     }
                 }
             }
@@ -224,9 +263,22 @@ __global__ void __launch_bounds__(BLOCK, BLOCK != 256 ? 1 : SPH != RT_SPH_DIRECT
         }
         if (__ballot_sync(FULL, L.have) == 0u) break;
 
+        // ---- 1b. fused passes: a pixel's pass p continues the sums its pass p-1 stored; the alpha sum
+        //          (1 + samples so far, pixel_alpha) tags the record.  Not there yet: look again next time
+        //          round — the lane never blocks, so the producer (which may sit in this very warp) runs on ----
+        if (L.have && (L.ctl & RT_LANE_WAIT)) {
+            const RtFloat4* ac = P.queues[(L.ctl >> 16) & 0xffu].accum;
+            const float4    a  = accum_load(&ac[L.out_index]);
+            if (a.w == pixel_alpha(1.0f, L.sample)) {
+                L.acc_r = a.x; L.acc_g = a.y; L.acc_b = a.z;
+                L.ctl &= ~RT_LANE_WAIT;
+            }
+        }
+        const bool ready = L.have && !(L.ctl & RT_LANE_WAIT);
+
         // ---- 2. one ray segment per live lane (sample start, World::hit, scatter, accumulate) ----
         bool sample_done = false;
-        if (L.have && trace) {
+        if (ready && trace) {
             sample_done = trace_segment<FAST, SPH, TRIS>(L, P, G, sph, sph_r2, cv, tri_plane);
             ++segments;
         }
@@ -240,17 +292,20 @@ __global__ void __launch_bounds__(BLOCK, BLOCK != 256 ? 1 : SPH != RT_SPH_DIRECT
             continue;
         }
 
-        // ---- 3b. resolve + pack when the pixel is complete ----
-        if (L.have && (!trace || L.sample >= P.spp)) {
+        // ---- 3b. the pixel's pass is complete: hand the sums on and/or resolve + pack ----
+        const uint32_t pass     = L.ctl & 0xffffu;
+        const int32_t  pass_end = (int32_t)((pass + 1u) * (uint32_t)(P.spp > 0 ? P.spp : 0));
+        if (ready && (!trace || L.sample >= pass_end)) {
+            RtFloat4*  ac   = P.queues[(L.ctl >> 16) & 0xffu].accum;
+            const bool last = pass + 1u == passes;
             // alpha: 1.0 (or the accumulator's) + one per sample; depth <= 0 still adds spp black samples
-            const float a0    = (P.flags & RT_FLAG_ACCUM_IN) ? P.accum[L.out_index].w : 1.0f;
-            const float acc_a = pixel_alpha(a0, P.spp > 0 ? P.spp : 0);
-            if (P.flags & RT_FLAG_ACCUM_OUT) {
-                float4 a = make_float4(L.acc_r, L.acc_g, L.acc_b, acc_a);
-                *reinterpret_cast<float4*>(&P.accum[L.out_index]) = a;
-            }
-            if (!(P.flags & RT_FLAG_NO_RESOLVE))
-                P.out[L.out_index] = resolve_pixel<FAST>(L.acc_r, L.acc_g, L.acc_b, acc_a, P.resolve_spp);
+            const float a0    = (P.flags & RT_FLAG_ACCUM_IN) ? ac[L.out_index].w : 1.0f;
+            const float acc_a = pixel_alpha(a0, pass_end);
+            if (!last || (P.flags & RT_FLAG_ACCUM_OUT))
+                accum_store(&ac[L.out_index], make_float4(L.acc_r, L.acc_g, L.acc_b, acc_a));
+            if (last ? !(P.flags & RT_FLAG_NO_RESOLVE) : (P.flags & RT_FLAG_RESOLVE_EACH_PASS) != 0u)
+                P.out[L.out_index] = resolve_pixel<FAST>(L.acc_r, L.acc_g, L.acc_b, acc_a,
+                                                         last ? P.resolve_spp : P.sample_begin + pass_end);
             L.have = false;
         }
     }

@@ -124,6 +124,20 @@ enum : uint32_t {
     RT_FLAG_GROUP_CULL   = 1u << 6,   // run the CULL kernels (block C): same hits, fewer sphere tests
     RT_FLAG_SAMPLE_ITEMS = 1u << 5,   // work items are (pixel, sample) pairs; colours go to `samples`, the
                                       // ordered sum + resolve is done by rt_resolve_samples_kernel
+    RT_FLAG_RESOLVE_EACH_PASS = 1u << 7,   // fused progressive passes: store the resolved pixel after every pass
+};
+
+// One work queue of a launch.  Queue 0 is the launch's own shard; further entries are the shards
+// of OTHER GPUs rendering the same frame, whose work counter (and float4 sums) live in their
+// memory and are reached through peer / CUDA-IPC mappings: when a warp finds its own queue empty
+// it takes slabs from the other queues (atomicAdd at system scope over NVLink) — the tail of the
+// frame is stolen by whichever GPU is free.
+#define RT_MAX_QUEUES 8u
+struct RtQueue {
+    unsigned int* work_counter;   // next unassigned slot of this shard (reset by its owner before every frame)
+    RtFloat4*     accum;          // this shard's float4 sums (fused passes), indexed like `out`
+    uint32_t      tile_first;     // shard index: the queue's tiles are rt_shard_tile(tile_first, tile_stride, j)
+    uint32_t      n_tiles;
 };
 
 // Everything one render launch needs (passed by value as a __grid_constant__).
@@ -131,7 +145,7 @@ struct RtFrameParams {
     RtCameraData camera;
     float    wm1, hm1;       // (W-1) as f32, (H-1) as f32: the divisors of common.rs:335-336
     uint32_t width, height;
-    int32_t  spp;            // samples traced by this launch (common.rs:334)
+    int32_t  spp;            // samples traced per pixel and pass by this launch (common.rs:334)
     int32_t  depth;          // max_ray_bounces (common.rs:267)
     int32_t  sample_begin;   // index of this launch's first sample (progressive passes)
     int32_t  resolve_spp;    // divisor of the resolve (common.rs:345-348)
@@ -141,13 +155,21 @@ struct RtFrameParams {
     //   rt_shard_tile(tile_first, tile_stride, j), j = 0 .. n_tiles-1   (tile_rows rows each).
     uint32_t tile_rows, tile_first, tile_stride, n_tiles;
     uint32_t reserve;        // pixel slots a warp takes per atomicAdd (multiple of 32)
-    uint32_t pad0;
+    // Progressive passes fused into ONE launch (1 = a plain frame).  The work space is pass-major:
+    // slot s belongs to pass s / (slots per pass) and traces samples sample_begin + pass*spp ...
+    // A pixel's pass p starts from the float4 sums its pass p-1 left in `accum` (whichever lane,
+    // warp or GPU traced it): the alpha channel of the sums counts the samples (1 + p*spp), so the
+    // 16-byte record carries its own "ready" tag, and a lane whose pixel is not ready yet simply
+    // retries in its next loop iteration.  No drain between passes, one ramp-up per frame.
+    uint32_t passes;
     uint32_t* out;           // RGBA8 as u32, full frame or compact (RT_FLAG_COMPACT_OUT)
     RtFloat4* accum;         // optional float4 sums, same indexing as out
     unsigned long long* ray_counter;   // += number of World::hit calls
     unsigned int* work_counter;        // zeroed before launch
+    unsigned int* steal_counter;       // += slots taken from other shards' queues (may be null)
     // RT_FLAG_SAMPLE_ITEMS: colour of sample s of the pixel with output index i at samples[s*sample_stride + i]
     RtFloat4* samples;
     uint32_t  sample_stride;
-    uint32_t  pad1;
+    uint32_t  n_queues;      // >= 1
+    RtQueue   queues[RT_MAX_QUEUES];   // [0] = the launch's own shard (work_counter / accum above), then the peers
 };

@@ -78,34 +78,45 @@ def gather_frame(local: torch.Tensor, width: int, height: int, tile_rows: int, r
 class ShardedRenderer:
     """One rank's share of a tile-sharded frame, device-resident.
 
-    Every rank renders tiles rank, rank+world, ... of the frame — optionally as several
-    progressive passes through a float4 accumulator that never leaves the GPU — and the finished
-    RGBA8 tiles end up on rank 0.  Two gathers:
+    Every rank renders its row tiles of the frame (rt_shard_tile) — progressive passes fused into one
+    persistent launch, the float4 sums never leaving the GPU — and the finished RGBA8 tiles end up on
+    rank 0.  Two gathers:
 
       gather="peer" (default for world > 1): rank 0 owns the frame (rt_device_alloc) and exports
           it through CUDA IPC; the other ranks map it and their render kernels STORE their tiles
           straight into rank 0's memory over NVLink (RT_OPT_FULL_FRAME_OUT) — the gather is
           fused into the pack step of the kernel.  A one-element all-reduce enqueued after the
           kernels orders rank 0's read after everybody's stores; it carries no frame data.
+          With steal=True every rank also exports its shard block (work counter + sums); a GPU whose
+          own queue is empty takes slabs of the other GPUs' queues over NVLink (static deal + work
+          stealing of the tail, rt_types.h RtQueue).
       gather="nccl": every rank packs its tiles into a compact buffer; one dist.gather to rank 0
           and a permuting view reassemble the frame (also the gloo/CPU-testable path).
 
     All kernels, the collective and the optional D2H are enqueued on torch's current CUDA
     stream, so CUDA events recorded on that stream bracket the whole step.
+
+    Frame lifetime (peer gather): the frame returned by render() — the pinned host tensor or the raw
+    device address — is valid until the NEXT render() call on any rank; every render() therefore
+    starts with a token all-reduce, which rank 0 joins only after its previous D2H, so no rank can
+    store pixels of frame k+1 into a frame rank 0 is still copying out.
     """
 
     def __init__(self, rt, handle, width: int, height: int, rank: int = 0, world: int = 1,
-                 tile_rows: int = 16, device=None, gather: Optional[str] = None):
+                 tile_rows: int = 16, device=None, gather: Optional[str] = None, steal: bool = True):
         self.rt, self.handle = rt, handle
         self.width, self.height, self.rank, self.world, self.tile_rows = width, height, rank, world, tile_rows
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.gather = gather or ("peer" if world > 1 else "nccl")
         assert self.gather in ("peer", "nccl")
-        self.accum: Optional[torch.Tensor] = None
         self.host_frame = (torch.empty((height, width), dtype=torch.int32).pin_memory() if rank == 0 else None)
         self.frame_ptr = 0        # peer mode: rank 0's frame (own allocation on rank 0, IPC mapping elsewhere)
         self._owns_frame = False
         self.peer_error = None
+        self.block_ptr = 0        # this rank's shard block (work stealing)
+        self._peer_blocks = {}    # rank -> mapped address of its shard block
+        self.queues = None        # [(block address, shard index)] own first, then (rank+1), (rank+2), ...
+        self.steal = False
         if self.gather == "peer" and world > 1:
             # Map rank 0's frame into every rank.  CUDA IPC can be unavailable (containers without a
             # shared IPC namespace, no peer access): all ranks then agree to use the NCCL gather — a
@@ -140,6 +151,8 @@ class ShardedRenderer:
                 self.token.zero_()
                 self.local = None
                 self.staging = None
+                if steal and world <= 8 and not os.environ.get("RT_DISABLE_STEAL"):
+                    self._exchange_blocks()
         if not (self.gather == "peer" and world > 1):
             self.gather = "nccl"
             self.local = alloc_compact(width, height, tile_rows, world, self.device)
@@ -147,50 +160,85 @@ class ShardedRenderer:
             self.staging = (torch.empty((world, j * tile_rows * width), dtype=torch.int32, device=self.device)
                             if (world > 1 and rank == 0) else None)
 
+    def _exchange_blocks(self):
+        """Every rank allocates its shard block, marks its queue empty, and maps everybody else's."""
+        rt = self.rt
+        ok, mine = 1, None
+        try:
+            self.block_ptr = rt.device_alloc(rt.shard_block_bytes(self.width, self.height))
+            rt.shard_block_init(self.block_ptr)
+            mine = rt.ipc_export(self.block_ptr)
+        except rt.RenderError as e:
+            ok, self.peer_error = 0, str(e)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine)
+        if ok:
+            try:
+                for r, h in enumerate(handles):
+                    if r == self.rank:
+                        continue
+                    if h is None:
+                        raise rt.RenderError(f"rank {r} could not export its shard block")
+                    self._peer_blocks[r] = rt.ipc_open(h)
+            except rt.RenderError as e:
+                ok, self.peer_error = 0, str(e)
+        t = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)           # also: every block is initialised before anyone may raid it
+        if int(t.item()) == 0:
+            self._release_blocks()
+            return
+        order = [(self.rank + i) % self.world for i in range(self.world)]
+        self.queues = [((self.block_ptr if r == self.rank else self._peer_blocks[r]), r) for r in order]
+        self.steal = True
+
+    def _release_blocks(self):
+        for p in self._peer_blocks.values():
+            self.rt.ipc_close(p)
+        self._peer_blocks = {}
+        self.queues, self.steal = None, False
+
     def close(self):
-        if self.frame_ptr:
+        if self.frame_ptr or self.block_ptr:
             torch.cuda.synchronize(self.device)
-            if self._owns_frame:
-                if self.world > 1:
-                    dist.barrier()            # nobody may still be storing into the frame
-                self.rt.device_free(self.frame_ptr)
-            else:
+            if self.world > 1:
+                dist.barrier()                # nobody may still be storing into the frame or raiding a queue
+            self._release_blocks()
+            if self.frame_ptr and not self._owns_frame:
                 self.rt.ipc_close(self.frame_ptr)
-                dist.barrier()
-            self.frame_ptr = 0
+            if self.world > 1:
+                dist.barrier()                # all mappings are closed before their owners free the memory
+            if self.frame_ptr and self._owns_frame:
+                self.rt.device_free(self.frame_ptr)
+            if self.block_ptr:
+                self.rt.device_free(self.block_ptr)
+            self.frame_ptr = self.block_ptr = 0
 
     def render(self, spp: int, depth: int, passes: int = 1, seed: Optional[int] = None, fast_math: bool = False,
-               fixed_jitter: bool = False, to_host: bool = False, count_rays: bool = False, group_cull: bool = False):
+               fixed_jitter: bool = False, to_host: bool = False, count_rays: bool = False, group_cull: bool = False,
+               stats=None):
         """Returns (frame, rays).  frame: on rank 0 the [H, W] int32 RGBA8 frame — the pinned host
         tensor when to_host, else a device tensor (nccl gather) or the raw device address of the
         frame (peer gather); None on the other ranks.  rays: this rank's ray-segment count when
-        count_rays (that mode synchronises after every pass), else 0."""
+        count_rays (that mode synchronises the stream), else 0."""
         rt = self.rt
         assert passes >= 1 and spp % passes == 0, "spp must divide evenly into passes"
         peer = self.gather == "peer"
-        if passes > 1 and self.accum is None:
-            n = self.width * self.height if peer else self.local.numel()
-            self.accum = torch.empty((n, 4), dtype=torch.float32, device=self.device)
         tstream = torch.cuda.current_stream(self.device)
         stream = tstream.cuda_stream
+        if peer:
+            dist.all_reduce(self.token)       # frame-reuse fence (see the class docstring)
         out_ptr = self.frame_ptr if peer else self.local.data_ptr()
-        per, rays = spp // passes, 0
-        for p in range(passes):
-            last = p == passes - 1
-            o = rt.Options(per, depth, sample_begin=p * per, resolve_spp=spp, fast_math=fast_math,
-                           fixed_jitter=fixed_jitter, tile_rows=self.tile_rows, shard_index=self.rank,
-                           shard_count=self.world, accum_in=p > 0, accum_out=not last, no_resolve=not last,
-                           full_frame_out=peer, group_cull=group_cull)
-            if seed is not None:
-                o.seed = seed
-            st = rt.RenderStats() if count_rays else None
-            rt.render_device(self.handle, o, self.width, self.height, out_ptr,
-                             self.accum.data_ptr() if self.accum is not None else 0, stream, st)
-            if st is not None:
-                rays += st.rays
+        o = rt.Options(spp, depth, passes=passes, resolve_spp=spp, fast_math=fast_math, fixed_jitter=fixed_jitter,
+                       tile_rows=self.tile_rows, shard_index=self.rank, shard_count=self.world,
+                       full_frame_out=peer, group_cull=group_cull, peer_queues=self.queues if self.steal else None)
+        if seed is not None:
+            o.seed = seed
+        st = stats if stats is not None else (rt.RenderStats() if count_rays else None)
+        rt.render_device(self.handle, o, self.width, self.height, out_ptr, 0, stream, st)
+        rays = st.rays if st is not None else 0
         if peer:
             # stream-ordered completion fence: rank 0's all-reduce kernel cannot finish before every
-            # rank has launched its own, i.e. before every rank's render kernels have completed
+            # rank has launched its own, i.e. before every rank's render kernel has completed
             dist.all_reduce(self.token)
             frame = self.frame_ptr if self.rank == 0 else None
             if to_host and self.rank == 0:

@@ -35,7 +35,9 @@ def test_reference_struct_layouts(rt):
     assert C.sizeof(rt._ColorU8) == 4
     assert C.sizeof(rt._CFramebuffer) == 24 and rt._CFramebuffer.pixels.offset == 16
     assert C.sizeof(rt._WorldHandle) == 16 and rt._WorldHandle.camera.offset == 8
-    assert rt.lib().rt_abi_version() == 1
+    assert rt.lib().rt_abi_version() == 2
+    # the Python mirrors of the additive structs are the header's layouts (ABI version 2)
+    assert C.sizeof(rt.RenderStats) == 72 and C.sizeof(rt._RenderOptions) == 72 and C.sizeof(rt.PeerQueue) == 16
 
 
 def test_reference_header_is_source_compatible(tmp_path):

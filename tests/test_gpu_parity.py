@@ -410,7 +410,7 @@ def test_stochastic_render_agrees_with_the_reference_serial_stream(gpu_rt, ob, s
     <= 1.25 x RMSE of two independent oracle renders at the same spp (both are differences of
     two independent N-spp estimates), and mean colour within 0.5/255."""
     rt = gpu_rt
-    W, H, spp = 200, 112, 64
+    W, H, spp = 400, 224, 50          # BASELINE config 1 as src/main.rs renders it (main.rs:86-99)
     h = cases.product_scene(rt, scenes, "default", cases.LOOK_AT_CLI)
     cam, world = cases.oracle_scene(ob, scenes, "default", cases.LOOK_AT_CLI)
     got, _ = _render(rt, h, W, H, spp, 8)
@@ -512,6 +512,205 @@ def test_c3_c5_reduced_spp_full_resolution_bands(gpu_rt, ob, scenes):
         assert st.resident == 1 and st.filtered == 1 and st.rays == rays and np.array_equal(got, want), key
 
 
+def test_c1_full_config_equals_oracle(gpu_rt, ob, scenes):
+    """BASELINE config 1 exactly as src/main.rs renders it (main.rs:86-99): world.txt, new_look_at camera,
+    400x224, 50 spp, depth 8 — bit-exact pixels and ray count against the oracle."""
+    rt = gpu_rt
+    W, H, spp, depth = 400, 224, 50, 8
+    h = cases.product_scene(rt, scenes, "default", cases.LOOK_AT_CLI)
+    cam, world = cases.oracle_scene(ob, scenes, "default", cases.LOOK_AT_CLI)
+    got, st = _render(rt, h, W, H, spp, depth)
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    assert st.rays == rays and np.array_equal(got, want)
+
+
+def test_c3_full_config_band_equals_oracle(gpu_rt, ob, scenes):
+    """BASELINE config 3 at its REAL size — 1,000 spheres, 1920x1080, 256 spp, depth 8: the whole frame on the
+    GPU (sample items, 8 chunks of 32 spp under the 1 GiB sample-buffer cap), and one full-width 16-row tile
+    of it against the oracle (per-sample RNG: a band of the frame is exactly that band).  Bit-exact."""
+    rt = gpu_rt
+    W, H, spp, depth = 1920, 1080, 256, 8
+    text = scenes.c3_world()
+    h = rt.load_world(text)
+    got, st = _render(rt, h, W, H, spp, depth, pinned=True)
+    assert st.sample_items == 1 and st.launches == 16 and st.filtered == 1 and st.samples == W * H * spp
+    cam, world = ob.parse_input(text)
+    r0, r1 = 640, 656                                     # tile 40: small spheres, ground and sky reflections
+    want, rays_band, _ = ob.ray_trace(world, cam, W, H, spp, depth, rows=(r0, r1))
+    assert np.array_equal(got[r0:r1], want[r0:r1])
+    # the same tile alone, through the shard interface: identical pixels, and its ray count is the oracle's
+    fb = rt.Framebuffer(W, H)
+    s1 = rt.RenderStats()
+    rt.render_with_options(fb, h, rt.Options(spp, depth, tile_rows=16, shard_index=40, shard_count=68), s1)
+    assert s1.rays == rays_band and np.array_equal(fb.pixels[r0:r1], want[r0:r1])
+
+
+def test_c5_full_config_band_equals_oracle(gpu_rt, ob, scenes):
+    """BASELINE config 5 at its REAL size — 8,000 spheres + 2,000 triangles, 1280x720, 16 spp, depth 16:
+    whole frame on the GPU, one full-width 16-row tile against the oracle.  Bit-exact."""
+    rt = gpu_rt
+    W, H, spp, depth = 1280, 720, 16, 16
+    text = scenes.c5_world()
+    h = rt.load_world(text)
+    got, st = _render(rt, h, W, H, spp, depth, pinned=True)
+    assert st.resident == 1 and st.filtered == 1 and st.samples == W * H * spp
+    cam, world = ob.parse_input(text)
+    r0, r1 = 400, 416
+    want, rays_band, _ = ob.ray_trace(world, cam, W, H, spp, depth, rows=(r0, r1))
+    assert np.array_equal(got[r0:r1], want[r0:r1])
+    fb = rt.Framebuffer(W, H)
+    s1 = rt.RenderStats()
+    rt.render_with_options(fb, h, rt.Options(spp, depth, tile_rows=16, shard_index=25, shard_count=45), s1)
+    assert s1.rays == rays_band and np.array_equal(fb.pixels[r0:r1], want[r0:r1])
+
+
+def test_c4_geometry_16_fused_passes_equal_oracle(gpu_rt, ob, scenes):
+    """BASELINE config 4's shape — 3840x2160, 16 progressive passes — at 1 spp per pass: ONE persistent launch
+    traces all 16 passes (pass-major queue, sums through HBM), and the frame is the oracle's 16-spp frame."""
+    rt = gpu_rt
+    W, H, depth = 3840, 2160, 8
+    h = rt.load_world(scenes.default_world())
+    got, st = _render(rt, h, W, H, 16, depth, pinned=True, passes=16)
+    assert st.launches == 1 and st.passes_fused == 16
+    cam, world = ob.parse_input(scenes.default_world())
+    want, rays, _ = ob.ray_trace(world, cam, W, H, 16, depth)
+    assert st.rays == rays and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("key,W,H,spp,passes,depth", [("default", 333, 170, 12, 4, 8), ("example", 200, 120, 8, 8, 8),
+                                                      ("default", 64, 36, 6, 2, 1), ("c3", 96, 54, 4, 2, 8)])
+def test_fused_passes_equal_single_pass_and_oracle_sums(gpu_rt, ob, scenes, key, W, H, spp, passes, depth):
+    """RtRenderOptions.passes: k passes in one launch == one pass of the total, bit for bit — frame, ray count
+    and (accum_out) the float4 sums; RT_OPT_RESOLVE_EACH_PASS changes nothing in the final frame; shards too."""
+    import torch
+    rt = gpu_rt
+    text = cases.scene_text(scenes, key)
+    h = rt.load_world(text)
+    cam, world = ob.parse_input(text)
+    want, rays, want_acc = ob.ray_trace(world, cam, W, H, spp, depth, want_accum=True)
+    got, st = _render(rt, h, W, H, spp, depth, passes=passes, sample_items=False)
+    assert st.passes_fused == passes and st.launches == 1 and st.rays == rays and np.array_equal(got, want)
+    got, st = _render(rt, h, W, H, spp, depth, passes=passes, resolve_each_pass=True, sample_items=False)
+    assert st.passes_fused == passes and np.array_equal(got, want)
+    accum = torch.full((H, W, 4), 7.0, dtype=torch.float32, device="cuda")       # stale contents must not matter
+    out = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    s2 = rt.RenderStats()
+    rt.render_device(h, rt.Options(spp, depth, passes=passes, accum_out=True, sample_items=False), W, H, out.data_ptr(),
+                     accum.data_ptr(), 0, s2)
+    assert s2.passes_fused == passes and s2.rays == rays
+    assert np.array_equal(out.cpu().numpy().view(np.uint8).reshape(H, W, 4), want)
+    assert np.array_equal(accum.cpu().numpy(), want_acc)
+    fb = rt.Framebuffer(W, H)
+    for i in range(3):
+        rt.render_with_options(fb, h, rt.Options(spp, depth, passes=passes, shard_index=i, shard_count=3, tile_rows=8,
+                                                 sample_items=False))
+    assert np.array_equal(fb.pixels, want)
+    # sample items / continuing an accumulator cannot be fused: the total is traced as one pass, same bits
+    got, st = _render(rt, h, W, H, spp, depth, passes=passes, sample_items=True)
+    assert st.passes_fused == 0 and st.sample_items == 1 and np.array_equal(got, want)
+
+
+def _blocks(rt, W, H, n):
+    import torch
+    b = [torch.zeros(rt.shard_block_bytes(W, H), dtype=torch.uint8, device="cuda") for _ in range(n)]
+    torch.cuda.synchronize()           # the library renders on its own stream
+    return b
+
+
+@pytest.mark.parametrize("passes", [1, 4])
+def test_work_stealing_queues_on_one_gpu(gpu_rt, ob, scenes, passes):
+    """Cross-GPU work stealing, exercised deterministically on ONE device: three shard blocks whose owners
+    never start (their counters stay 0 = 'everything unassigned'); the launch of shard 0 renders its own
+    tiles, then raids queues 2 and 1 until the whole frame is done — every stolen pixel-pass reads and
+    writes the sums in its victim's block.  Frame and ray count equal the oracle's."""
+    import torch
+    rt = gpu_rt
+    W, H, spp, depth = 200, 117, 8, 8
+    text = scenes.example_world()
+    h = rt.load_world(text)
+    cam, world = ob.parse_input(text)
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    blocks = _blocks(rt, W, H, 3)
+    out = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    st = rt.RenderStats()
+    o = rt.Options(spp, depth, passes=passes, tile_rows=8, shard_index=0, shard_count=3, full_frame_out=True,
+                   peer_queues=[(blocks[0].data_ptr(), 0), (blocks[2].data_ptr(), 2), (blocks[1].data_ptr(), 1)])
+    rt.render_device(h, o, W, H, out.data_ptr(), 0, 0, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(np.uint8).reshape(H, W, 4), want)
+    assert st.rays == rays and st.passes_fused == (passes if passes > 1 else 0)
+    per_tile = ((W + 7) // 8) * 2 * 32                       # slots of one 8-row tile
+    tiles = [len(rt.shard_tiles(H, 8, i, 3)) for i in range(3)]
+    assert st.stolen_slots == (tiles[1] + tiles[2]) * per_tile * passes
+    # afterwards every queue reads 'empty': a second launch of another shard finds nothing to steal
+    out2 = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    o2 = rt.Options(spp, depth, passes=passes, tile_rows=8, shard_index=1, shard_count=3, full_frame_out=True,
+                    peer_queues=[(blocks[1].data_ptr(), 1), (blocks[2].data_ptr(), 2), (blocks[0].data_ptr(), 0)])
+    s2 = rt.RenderStats()
+    rt.render_device(h, o2, W, H, out2.data_ptr(), 0, 0, s2)
+    torch.cuda.synchronize()
+    rows = [r for r0, r1 in rt.shard_tiles(H, 8, 1, 3) for r in range(r0, r1)]
+    got2 = out2.cpu().numpy().view(np.uint8).reshape(H, W, 4)
+    assert s2.stolen_slots == 0 and np.array_equal(got2[rows], want[rows])
+    other = [r for r in range(H) if r not in rows]
+    assert not got2[other].any()
+
+
+def test_work_stealing_rejects_bad_queue_tables(gpu_rt, scenes):
+    import torch
+    rt = gpu_rt
+    h = rt.load_world(scenes.default_world())
+    blocks = _blocks(rt, 64, 32, 2)
+    out = torch.zeros((32, 64), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    q = [(blocks[0].data_ptr(), 0), (blocks[1].data_ptr(), 1)]
+    with pytest.raises(rt.RenderError, match="full-frame"):
+        rt.render_device(h, rt.Options(1, 1, shard_index=0, shard_count=2, peer_queues=q), 64, 32, out.data_ptr(), 0, 0)
+    with pytest.raises(rt.RenderError, match="every shard"):
+        rt.render_device(h, rt.Options(1, 1, shard_index=0, shard_count=3, full_frame_out=True, peer_queues=q), 64, 32,
+                         out.data_ptr(), 0, 0)
+    with pytest.raises(rt.RenderError, match="own block"):
+        rt.render_device(h, rt.Options(1, 1, shard_index=0, shard_count=2, full_frame_out=True,
+                                       peer_queues=[(blocks[1].data_ptr(), 1), (blocks[1].data_ptr(), 1)]), 64, 32,
+                         out.data_ptr(), 0, 0)
+
+
+def test_progressive_frame_on_another_device(gpu_rt, ob, scenes):
+    """rt_render_progressive with options->device != the caller's current device: the sums live on the device
+    that renders, and the caller's current device is left alone."""
+    import torch
+    rt = gpu_rt
+    if rt.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    W, H = 96, 54
+    h = rt.load_world(scenes.default_world())
+    cam, world = ob.parse_input(scenes.default_world())
+    torch.cuda.set_device(0)
+    fb = rt.Framebuffer(W, H)
+    assert rt.render_progressive(fb, h, rt.Options(2, 8, device=1)) == 2
+    assert rt.render_progressive(fb, h, rt.Options(3, 8, device=1)) == 5
+    want, _, _ = ob.ray_trace(world, cam, W, H, 5, 8)
+    assert np.array_equal(fb.pixels, want) and torch.cuda.current_device() == 0
+
+
+def test_unbalanced_shards_are_rebalanced_by_stealing(gpu_rt, scenes):
+    """Two devices, two tiles: the upper half of the frame (sky, one segment per sample) and the lower half (the
+    ground, long paths).  The device that owns the cheap tile finishes early and raids the other one's queue."""
+    rt = gpu_rt
+    if rt.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    W, H = 1024, 512
+    h = rt.load_world(scenes.default_world())
+    full, st1 = _render(rt, h, W, H, 32, 8)
+    for passes in (1, 4):
+        got, st = _render(rt, h, W, H, 32, 8, n_devices=2, tile_rows=256, passes=passes)
+        assert st.devices == 2 and st.peer_gather == 1 and st.rays == st1.rays and np.array_equal(got, full)
+        assert st.stolen_slots > 0, "the device with the sky tile should have raided the ground tile's queue"
+
+
 def test_one_process_many_gpus_peer_store_gather(gpu_rt, ob, scenes):
     """render_with_options(n_devices=N): device d renders tiles d, d+N, ... and stores them
     straight into device 0's frame (peer mapping); the frame equals the single-GPU frame."""
@@ -551,7 +750,9 @@ def _dist_worker(rank, world, port, gather, q):
     W, H = 333, 170                                  # ragged: last tile is partial, tiles % world != 0
     r = multi.ShardedRenderer(rt, h, W, H, rank, world, tile_rows=16, gather=gather)
     assert r.gather == expect, (r.gather, expect, r.peer_error)
+    assert r.steal == (expect == "peer")                         # shard blocks exchanged over CUDA IPC
     frame, rays = r.render(8, 8, passes=2, to_host=True, count_rays=True)
+    frame = frame.clone()                                        # the host frame is reused by the next render()
     frame2, _ = r.render(8, 8, passes=1, to_host=True)          # single pass == two progressive passes
     t = torch.tensor([rays], dtype=torch.int64, device="cuda")
     dist.all_reduce(t)
