@@ -56,6 +56,8 @@ typedef struct RtRenderStats {
   uint32_t culled;      /* 1: the CULL kernels ran (RT_OPT_GROUP_CULL) */
   uint32_t passes_fused;/* progressive passes traced by ONE persistent launch (0 or 1: a plain frame) */
   uint32_t stolen_slots;/* pixel slots this call's GPU(s) took from other GPUs' shards (work stealing) */
+  uint32_t paths_per_lane; /* 2: the FILTER kernels ran with two paths per lane (one sphere load serves two rays) */
+  uint32_t reserved;
 } RtRenderStats;
 
 /* One shard's block for cross-GPU work stealing (rt_shard_block_bytes bytes of device memory owned by

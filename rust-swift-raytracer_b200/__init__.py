@@ -70,7 +70,8 @@ class RenderStats(C.Structure):
                 ("smem_bytes", C.c_uint32), ("resident", C.c_uint32), ("block", C.c_uint32),
                 ("devices", C.c_uint32), ("peer_gather", C.c_uint32), ("filtered", C.c_uint32),
                 ("sample_items", C.c_uint32), ("culled", C.c_uint32),
-                ("passes_fused", C.c_uint32), ("stolen_slots", C.c_uint32)]
+                ("passes_fused", C.c_uint32), ("stolen_slots", C.c_uint32),
+                ("paths_per_lane", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -186,10 +187,11 @@ def lib() -> C.CDLL:
     L.rt_device_alloc.argtypes = [C.c_size_t]
     L.rt_device_free.restype = None
     L.rt_device_free.argtypes = [C.c_void_p]
-    L.rt_shard_block_bytes.restype = C.c_size_t
-    L.rt_shard_block_bytes.argtypes = [C.c_size_t, C.c_size_t]
-    L.rt_shard_block_init.restype = C.c_int
-    L.rt_shard_block_init.argtypes = [C.c_void_p]
+    if not _variant or hasattr(L, "rt_shard_block_bytes"):      # an A/B build of an older ABI may lack them
+        L.rt_shard_block_bytes.restype = C.c_size_t
+        L.rt_shard_block_bytes.argtypes = [C.c_size_t, C.c_size_t]
+        L.rt_shard_block_init.restype = C.c_int
+        L.rt_shard_block_init.argtypes = [C.c_void_p]
     L.rt_ipc_export.restype = C.c_int
     L.rt_ipc_export.argtypes = [C.c_void_p, C.c_char_p]
     L.rt_ipc_open.restype = C.c_void_p

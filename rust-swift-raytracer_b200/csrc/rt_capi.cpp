@@ -92,7 +92,7 @@ void export_stats(const rt::RenderStats& s, RtRenderStats* out, bool v2)
     out->launches = s.launches; out->grid = s.grid; out->smem_bytes = s.smem_bytes; out->resident = s.resident;
     out->block = s.block; out->devices = s.devices; out->peer_gather = s.peer_gather; out->filtered = s.filtered;
     out->sample_items = s.sample_items; out->culled = s.culled;
-    if (v2) { out->passes_fused = s.passes_fused; out->stolen_slots = s.stolen_slots; }
+    if (v2) { out->passes_fused = s.passes_fused; out->stolen_slots = s.stolen_slots; out->paths_per_lane = s.paths_per_lane; out->reserved = 0; }
 }
 
 template <class F>
@@ -396,11 +396,9 @@ static int write_any(Rust_CFramebuffer fb, const char* path, bool p6)
 {
     return guarded([&] {
         if (!fb.pixels) throw std::runtime_error("framebuffer.pixels is NULL");
-        rt::Framebuffer f;
-        f.width = fb.width; f.height = fb.height;
-        f.pixels.resize(fb.width * fb.height);
-        std::memcpy(f.pixels.data(), fb.pixels, fb.width * fb.height * 4);
-        if (!(p6 ? rt::write_image_p6(f, path) : rt::write_image(f, path))) throw std::runtime_error("cannot write image");
+        const rt::ColorU8* px = reinterpret_cast<const rt::ColorU8*>(fb.pixels);
+        if (!(p6 ? rt::write_image_p6(px, fb.width, fb.height, path) : rt::write_image(px, fb.width, fb.height, path)))
+            throw std::runtime_error("cannot write image");
     });
 }
 int rt_write_image(Rust_CFramebuffer fb, const char* path) { return write_any(fb, path, false); }

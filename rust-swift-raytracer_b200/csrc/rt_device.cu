@@ -64,6 +64,7 @@ struct DeviceContext {
     size_t       smem_optin = 0;
     cudaStream_t stream   = nullptr;
     cudaEvent_t  ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;
     CounterSlot* d_slots  = nullptr;
     CounterSlot* h_slot   = nullptr;   // pinned
     int          next_slot = 0;
@@ -206,7 +207,7 @@ struct ShardLaunch {
     int          grid = 0, block = 0;
     size_t       hot_bytes = 0, smem_limit = 0;
     bool         resident = false, filtered = false, culled = false, sample_items = false;
-    uint32_t     launches = 0, passes_fused = 0;
+    uint32_t     launches = 0, passes_fused = 0, paths_per_lane = 1;
     CounterSlot* slot = nullptr;
     uint32_t*    d_out = nullptr;
 };
@@ -287,7 +288,8 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     // is why it is reserved for scenes whose segments cost thousands of instructions.
     int32_t chunk_spp = opt.samples_per_pixel;       // samples per launch in sample-item mode
     {
-        const uint64_t lanes_max  = (uint64_t)ctx.num_sms * 2048u / 2u;          // 32 warps/SM at 64 registers
+        const uint64_t lanes_max  = (uint64_t)ctx.num_sms * 2048u / 2u;          // paths in flight: 32 warps/SM at 64 registers
+                                                                                 // (or 16 warps/SM carrying two paths per lane)
         const uint64_t pixels     = (uint64_t)L.n_tiles * opt.tile_rows * W;
         const uint64_t prims      = (uint64_t)scene.view.n_sph + scene.view.n_tri;
         const bool     want = opt.sample_items > 0 ||
@@ -389,8 +391,9 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     }
     L.hot_bytes = occ.hot_bytes;
     L.resident  = occ.resident != 0;
-    L.filtered  = occ.sph_mode != RT_SPH_DIRECT;
-    L.culled    = occ.sph_mode == RT_SPH_CULL;
+    L.filtered  = (occ.sph_mode & 0xff) != RT_SPH_DIRECT;
+    L.culled    = (occ.sph_mode & 0xff) == RT_SPH_CULL;
+    L.paths_per_lane = (uint32_t)(occ.sph_mode >> 8);
     L.block = occ.block;
     // with stealing every GPU may end up tracing any part of the frame: size the grid for the whole frame
     uint64_t frame_slots = slots;
@@ -493,8 +496,15 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
     // Pageable destination (what the reference's callers pass: UnsafeMutablePointer.allocate in
     // GameView.swift:125-129, a Vec in examples/c_raytracer.rs:53): the kernel stores its pixels into the
     // library's pinned staging frame the same way, and one memcpy hands them over — no D2H copy either.
+    // RT_PAGEABLE selects the way to a pageable frame (A/B measurements): zc = staged zero-copy (default),
+    // d2h = one D2H into the staging frame then memcpy, chunk = D2H in pieces overlapped with their memcpy.
+    static const int pageable_mode = [] {
+        const char* e = std::getenv("RT_PAGEABLE");
+        if (!e) return 0;
+        return !std::strcmp(e, "d2h") ? 1 : !std::strcmp(e, "chunk") ? 2 : 0;
+    }();
     bool staged_zero_copy = false;
-    if (want_zero_copy && !zero_copy && !is_pinned_or_device_accessible(host_pixels)) {
+    if (pageable_mode == 0 && want_zero_copy && !zero_copy && !is_pinned_or_device_accessible(host_pixels)) {
         ensure_stage(ctx, (size_t)W * H * 4);
         zero_copy = mapped_device_pointer(ctx.h_stage);
         staged_zero_copy = zero_copy != nullptr;
@@ -538,6 +548,27 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
                 f(first, L.compact ? (size_t)j * tile_px : first, count);
             }
         };
+        if (!direct && pageable_mode == 2 && opt.shard_count <= 1) {
+            // pieces of ~1 MiB: the memcpy of piece i runs while pieces i+1.. are still on their way
+            const size_t total = (size_t)W * H * 4, piece = (size_t)1 << 20;
+            const size_t n = (total + piece - 1) / piece;
+            while (ctx.ev_chunk.size() < n) {
+                cudaEvent_t e;
+                RT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx.ev_chunk.push_back(e);
+            }
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(d_out);
+            for (size_t i = 0; i < n; ++i) {
+                const size_t off = i * piece, cnt = std::min(piece, total - off);
+                RT_CUDA(cudaMemcpyAsync(ctx.h_stage + off, src + off, cnt, cudaMemcpyDeviceToHost, stream));
+                RT_CUDA(cudaEventRecord(ctx.ev_chunk[i], stream));
+            }
+            for (size_t i = 0; i < n; ++i) {
+                const size_t off = i * piece, cnt = std::min(piece, total - off);
+                RT_CUDA(cudaEventSynchronize(ctx.ev_chunk[i]));
+                std::memcpy(reinterpret_cast<unsigned char*>(host_pixels) + off, ctx.h_stage + off, cnt);
+            }
+        } else {
         for_each_piece([&](size_t frame_px, size_t dev_px, size_t count) {
             void* dst = direct ? (void*)(host32 + frame_px) : (void*)(ctx.h_stage + dev_px * 4);
             RT_CUDA(cudaMemcpyAsync(dst, d_out + dev_px, count * 4, cudaMemcpyDeviceToHost, stream));
@@ -547,6 +578,7 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
             for_each_piece([&](size_t frame_px, size_t dev_px, size_t count) {
                 std::memcpy(host32 + frame_px, ctx.h_stage + dev_px * 4, count * 4);
             });
+        }
     } else if (!user_stream) {
         RT_CUDA(cudaStreamSynchronize(stream));
     }
@@ -567,6 +599,7 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
             st.rays     = ctx.h_slot->rays;
             st.stolen_slots = ctx.h_slot->stolen;
             st.passes_fused = L.passes_fused;
+            st.paths_per_lane = L.paths_per_lane;
             st.launches = L.launches;
             st.sample_items = L.sample_items ? 1u : 0u;
             st.samples  = (opt.samples_per_pixel > 0 && opt.max_ray_bounces > 0)
@@ -733,6 +766,7 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
             st.rays += c.h_slot->rays;
             st.stolen_slots += c.h_slot->stolen;
             st.passes_fused = launches[d].passes_fused;
+            st.paths_per_lane = launches[d].paths_per_lane;
             st.launches += launches[d].launches;
             st.sample_items = launches[d].sample_items ? 1u : 0u;
             Options o = base; o.shard_index = (uint32_t)d;

@@ -100,6 +100,7 @@ struct RenderStats {
     uint32_t culled     = 0;     // 1: the CULL kernels ran (group bounds in front of the filter)
     uint32_t passes_fused = 0;   // progressive passes traced by one persistent launch (0/1: a plain frame)
     uint32_t stolen_slots = 0;   // pixel slots this GPU took from other GPUs' shards (cross-GPU work stealing)
+    uint32_t paths_per_lane = 1; // 2: every lane traced two paths and tested both rays against each sphere it loaded
 };
 
 // common.rs:289-294, extended.  The reference fields keep their names.
@@ -209,6 +210,8 @@ uint32_t shard_tile_count(uint32_t height, uint32_t tile_rows, uint32_t index, u
 // image.rs:59-81 (ASCII P3) and a binary P6 variant.  Return false on I/O failure.
 bool write_image(const Framebuffer& fb, const char* path);
 bool write_image_p6(const Framebuffer& fb, const char* path);
+bool write_image(const ColorU8* pixels, size_t width, size_t height, const char* path);      // no copy of the frame
+bool write_image_p6(const ColorU8* pixels, size_t width, size_t height, const char* path);
 
 // Device utilities
 int    device_count();

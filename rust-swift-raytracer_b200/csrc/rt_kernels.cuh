@@ -28,6 +28,8 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 
 namespace rt {
 
@@ -155,10 +157,16 @@ __device__ __forceinline__ void accum_store(RtFloat4* p, float4 v)
 #define RT_MIN_CTAS_FILTER 3  // FILTER kernels: 80 registers measured faster than 64 (the loop is FFMA-bound,
 #endif                        // not latency-bound: C3 fast 399 -> 369 ms, exact 439 -> 431 ms)
 
-template <bool FAST, bool SMEM, int BLOCK, int SPH, bool TRIS>
-__global__ void __launch_bounds__(BLOCK, BLOCK != 256 ? 1 : SPH != RT_SPH_DIRECT ? RT_MIN_CTAS_FILTER : RT_MIN_CTAS_SMALL) rt_render_kernel(const __grid_constant__ RtFrameParams P,
-                                                         const __grid_constant__ RtSceneView  G)
+// NP = paths per lane.  1: a lane traces one ray at a time.  2 (FILTER walk): a lane carries two independent
+// paths (two pixels, or two samples in sample-item mode) and tests BOTH rays against every sphere it loads —
+// half the shared-memory feed per ray-sphere test (rt_trace.cuh sphere_filter_group_n).  The doubled state
+// needs ~128 registers: two 256-thread CTAs per SM, or one 512-thread CTA when the lists fill shared memory.
+template <bool FAST, bool SMEM, int BLOCK, int SPH, bool TRIS, int NP>
+__global__ void __launch_bounds__(BLOCK, NP == 2 ? (BLOCK == 256 ? 2 : 1)
+                                         : BLOCK != 256 ? 1 : SPH != RT_SPH_DIRECT ? RT_MIN_CTAS_FILTER : RT_MIN_CTAS_SMALL)
+rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant__ RtSceneView G)
 {
+    static_assert(NP == 1 || (NP == 2 && SPH == RT_SPH_FILTER), "two paths per lane exist for the FILTER walk only");
     extern __shared__ __align__(128) unsigned char rt_smem[];
     __shared__ __align__(8) unsigned long long rt_mbar;
 
@@ -208,105 +216,148 @@ __global__ void __launch_bounds__(BLOCK, BLOCK != 256 ? 1 : SPH != RT_SPH_DIRECT
     // warp-uniform slab of reserved pixel slots
     uint32_t pool_next = 0, pool_end = 0;
 
-    Lane L;
-    L.have = false;
-    L.fcol = L.frow = 0.f;
-    L.pix_hash = L.out_index = 0u;
-    L.sample = 0; L.seg_left = 0; L.rng = 1u; L.pend_unit = false;
-    L.ctl = 0u;
-    L.acc_r = L.acc_g = L.acc_b = 0.f;
-    L.o = L.pend = L.thr = mk(0.f, 0.f, 0.f);
+    Lane L[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        L[p].have = false;
+        L[p].fcol = L[p].frow = 0.f;
+        L[p].pix_hash = L[p].out_index = 0u;
+        L[p].sample = 0; L[p].seg_left = 0; L[p].rng = 1u; L[p].pend_unit = false;
+        L[p].ctl = 0u;
+        L[p].acc_r = L[p].acc_g = L[p].acc_b = 0.f;
+        L[p].o = L[p].pend = L[p].thr = mk(0.f, 0.f, 0.f);
+    }
     uint32_t segments = 0;
 
     for (;;) {
-        // ---- 1. lanes without a pixel take the next slots of the warp's slab ----
-        uint32_t need = __ballot_sync(FULL, !L.have);
-        while (need && q < P.n_queues) {
-            if (pool_next == pool_end) {
-                const uint32_t total = P.queues[q].n_tiles * slots_per_tile * passes;
-                uint32_t       base  = 0;
-                if (lane == 0)
-                    base = P.n_queues > 1u ? atomicAdd_system(P.queues[q].work_counter, P.reserve)
-                                           : atomicAdd(P.queues[q].work_counter, P.reserve);
-                base = __shfl_sync(FULL, base, 0);
-                if (base >= total) { ++q; continue; }      // this shard has no unassigned work left: raid the next one
-                pool_next = base;
-                pool_end  = min(base + P.reserve, total);
-                if (q && lane == 0 && P.steal_counter) atomicAdd(P.steal_counter, pool_end - pool_next);
-            }
-            const uint32_t avail = pool_end - pool_next;
-            const uint32_t rank  = __popc(need & lt);
-            if (!L.have && rank < avail) {
-                uint32_t  item_sample, pass;
-                const uint32_t q_tiles = P.queues[q].n_tiles;
-                PixelSlot s = decode_slot(P, pool_next + rank, subtiles_x, chunks_per_strip, P.queues[q].tile_first, q_tiles,
-                                          q_tiles * slots_per_tile, item_sample, pass);
-                if (s.valid) {
-                    begin_pixel(L, P, s.column, P.height - 1u - s.image_row, s.out_index);   // common.rs:351 (flip)
-                    L.ctl = pass | (q << 16);
-                    if (items) {                       // one sample: sums start at 0, colour goes to the sample buffer
-                        L.sample    = (int32_t)item_sample;
-                        L.out_index = item_sample * P.sample_stride + s.out_index;
-                    } else {
-                        L.sample = (int32_t)(pass * (uint32_t)P.spp);
-                        if (pass > 0u) {
-                            L.ctl |= RT_LANE_WAIT;     // starts from the sums of the pixel's previous pass (step 1b)
-                        } else if (P.flags & RT_FLAG_ACCUM_IN) {
-                            RtFloat4 a = ld4(&P.queues[0].accum[s.out_index]);
-                            L.acc_r = a.x; L.acc_g = a.y; L.acc_b = a.z;      // a.w is re-read at the end
+        // ---- 1. paths without a pixel take the next slots of the warp's slab ----
+        bool any_have = false;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            Lane&    Lp   = L[p];
+            uint32_t need = __ballot_sync(FULL, !Lp.have);
+            while (need && q < P.n_queues) {
+                if (pool_next == pool_end) {
+                    const uint32_t total = P.queues[q].n_tiles * slots_per_tile * passes;
+                    uint32_t       base  = 0;
+                    if (lane == 0)
+                        base = P.n_queues > 1u ? atomicAdd_system(P.queues[q].work_counter, P.reserve)
+                                               : atomicAdd(P.queues[q].work_counter, P.reserve);
+                    base = __shfl_sync(FULL, base, 0);
+                    if (base >= total) { ++q; continue; }      // this shard has no unassigned work left: raid the next one
+                    pool_next = base;
+                    pool_end  = min(base + P.reserve, total);
+                    if (q && lane == 0 && P.steal_counter) atomicAdd(P.steal_counter, pool_end - pool_next);
+                }
+                const uint32_t avail = pool_end - pool_next;
+                const uint32_t rank  = __popc(need & lt);
+                if (!Lp.have && rank < avail) {
+                    uint32_t  item_sample, pass;
+                    const uint32_t q_tiles = P.queues[q].n_tiles;
+                    PixelSlot s = decode_slot(P, pool_next + rank, subtiles_x, chunks_per_strip, P.queues[q].tile_first, q_tiles,
+                                              q_tiles * slots_per_tile, item_sample, pass);
+                    if (s.valid) {
+                        begin_pixel(Lp, P, s.column, P.height - 1u - s.image_row, s.out_index);   // common.rs:351 (flip)
+                        Lp.ctl = pass | (q << 16);
+                        if (items) {                       // one sample: sums start at 0, colour goes to the sample buffer
+                            Lp.sample    = (int32_t)item_sample;
+                            Lp.out_index = item_sample * P.sample_stride + s.out_index;
+                        } else {
+                            Lp.sample = (int32_t)(pass * (uint32_t)P.spp);
+                            if (pass > 0u) {
+                                Lp.ctl |= RT_LANE_WAIT;     // starts from the sums of the pixel's previous pass (step 1b)
+                            } else if (P.flags & RT_FLAG_ACCUM_IN) {
+                                RtFloat4 a = ld4(&P.queues[0].accum[s.out_index]);
+                                Lp.acc_r = a.x; Lp.acc_g = a.y; Lp.acc_b = a.z;      // a.w is re-read at the end
+                            }
                         }
                     }
                 }
+                pool_next += min(avail, (uint32_t)__popc(need));
+                need = __ballot_sync(FULL, !Lp.have);
             }
-            pool_next += min(avail, (uint32_t)__popc(need));
-            need = __ballot_sync(FULL, !L.have);
+            any_have = any_have || Lp.have;
         }
-        if (__ballot_sync(FULL, L.have) == 0u) break;
+        if (__ballot_sync(FULL, any_have) == 0u) break;
 
         // ---- 1b. fused passes: a pixel's pass p continues the sums its pass p-1 stored; the alpha sum
         //          (1 + samples so far, pixel_alpha) tags the record.  Not there yet: look again next time
         //          round — the lane never blocks, so the producer (which may sit in this very warp) runs on ----
-        if (L.have && (L.ctl & RT_LANE_WAIT)) {
-            const RtFloat4* ac = P.queues[(L.ctl >> 16) & 0xffu].accum;
-            const float4    a  = accum_load(&ac[L.out_index]);
-            if (a.w == pixel_alpha(1.0f, L.sample)) {
-                L.acc_r = a.x; L.acc_g = a.y; L.acc_b = a.z;
-                L.ctl &= ~RT_LANE_WAIT;
+        bool ready[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            Lane& Lp = L[p];
+            if (Lp.have && (Lp.ctl & RT_LANE_WAIT)) {
+                const RtFloat4* ac = P.queues[(Lp.ctl >> 16) & 0xffu].accum;
+                const float4    a  = accum_load(&ac[Lp.out_index]);
+                if (a.w == pixel_alpha(1.0f, Lp.sample)) {
+                    Lp.acc_r = a.x; Lp.acc_g = a.y; Lp.acc_b = a.z;
+                    Lp.ctl &= ~RT_LANE_WAIT;
+                }
+            }
+            ready[p] = Lp.have && !(Lp.ctl & RT_LANE_WAIT);
+        }
+
+        // ---- 2. one ray segment per live path (sample start, World::hit, scatter, accumulate) ----
+        bool sample_done[NP];
+        if (NP == 1) {
+            sample_done[0] = false;
+            if (ready[0] && trace) {
+                sample_done[0] = trace_segment<FAST, SPH, TRIS>(L[0], P, G, sph, sph_r2, cv, tri_plane);
+                ++segments;
+            }
+        } else {
+            V3   o[NP], d[NP];
+            Hit  h[NP];
+            bool live = false;
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                sample_done[p] = false;
+                o[p] = mk(0.f, 0.f, 0.f);
+                d[p] = mk(NAN, NAN, NAN);                  // an idle path: never hits anything
+                if (ready[p] && trace) {
+                    d[p] = segment_begin<FAST>(L[p], P);
+                    o[p] = L[p].o;
+                    live = true;
+                    ++segments;
+                }
+            }
+            if (live) {
+                closest_hit_n<FAST, TRIS, NP>(sph, sph_r2, G.n_sph, G.n_sph_pad, tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, h);
+#pragma unroll
+                for (int p = 0; p < NP; ++p)
+                    if (ready[p] && trace) sample_done[p] = segment_end<FAST, SPH, TRIS>(L[p], G, sph, d[p], h[p]);
             }
         }
-        const bool ready = L.have && !(L.ctl & RT_LANE_WAIT);
 
-        // ---- 2. one ray segment per live lane (sample start, World::hit, scatter, accumulate) ----
-        bool sample_done = false;
-        if (ready && trace) {
-            sample_done = trace_segment<FAST, SPH, TRIS>(L, P, G, sph, sph_r2, cv, tri_plane);
-            ++segments;
-        }
-
-        // ---- 3a. sample items: hand the colour to the ordered-sum kernel ----
-        if (items) {
-            if (L.have && sample_done) {
-                *reinterpret_cast<float4*>(&P.samples[L.out_index]) = make_float4(L.acc_r, L.acc_g, L.acc_b, 1.0f);
-                L.have = false;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            Lane& Lp = L[p];
+            // ---- 3a. sample items: hand the colour to the ordered-sum kernel ----
+            if (items) {
+                if (Lp.have && sample_done[p]) {
+                    *reinterpret_cast<float4*>(&P.samples[Lp.out_index]) = make_float4(Lp.acc_r, Lp.acc_g, Lp.acc_b, 1.0f);
+                    Lp.have = false;
+                }
+                continue;
             }
-            continue;
-        }
 
-        // ---- 3b. the pixel's pass is complete: hand the sums on and/or resolve + pack ----
-        const uint32_t pass     = L.ctl & 0xffffu;
-        const int32_t  pass_end = (int32_t)((pass + 1u) * (uint32_t)(P.spp > 0 ? P.spp : 0));
-        if (ready && (!trace || L.sample >= pass_end)) {
-            RtFloat4*  ac   = P.queues[(L.ctl >> 16) & 0xffu].accum;
-            const bool last = pass + 1u == passes;
-            // alpha: 1.0 (or the accumulator's) + one per sample; depth <= 0 still adds spp black samples
-            const float a0    = (P.flags & RT_FLAG_ACCUM_IN) ? ac[L.out_index].w : 1.0f;
-            const float acc_a = pixel_alpha(a0, pass_end);
-            if (!last || (P.flags & RT_FLAG_ACCUM_OUT))
-                accum_store(&ac[L.out_index], make_float4(L.acc_r, L.acc_g, L.acc_b, acc_a));
-            if (last ? !(P.flags & RT_FLAG_NO_RESOLVE) : (P.flags & RT_FLAG_RESOLVE_EACH_PASS) != 0u)
-                P.out[L.out_index] = resolve_pixel<FAST>(L.acc_r, L.acc_g, L.acc_b, acc_a,
-                                                         last ? P.resolve_spp : P.sample_begin + pass_end);
-            L.have = false;
+            // ---- 3b. the pixel's pass is complete: hand the sums on and/or resolve + pack ----
+            const uint32_t pass     = Lp.ctl & 0xffffu;
+            const int32_t  pass_end = (int32_t)((pass + 1u) * (uint32_t)(P.spp > 0 ? P.spp : 0));
+            if (ready[p] && (!trace || Lp.sample >= pass_end)) {
+                RtFloat4*  ac   = P.queues[(Lp.ctl >> 16) & 0xffu].accum;
+                const bool last = pass + 1u == passes;
+                // alpha: 1.0 (or the accumulator's) + one per sample; depth <= 0 still adds spp black samples
+                const float a0    = (P.flags & RT_FLAG_ACCUM_IN) ? ac[Lp.out_index].w : 1.0f;
+                const float acc_a = pixel_alpha(a0, pass_end);
+                if (!last || (P.flags & RT_FLAG_ACCUM_OUT))
+                    accum_store(&ac[Lp.out_index], make_float4(Lp.acc_r, Lp.acc_g, Lp.acc_b, acc_a));
+                if (last ? !(P.flags & RT_FLAG_NO_RESOLVE) : (P.flags & RT_FLAG_RESOLVE_EACH_PASS) != 0u)
+                    P.out[Lp.out_index] = resolve_pixel<FAST>(Lp.acc_r, Lp.acc_g, Lp.acc_b, acc_a,
+                                                              last ? P.resolve_spp : P.sample_begin + pass_end);
+                Lp.have = false;
+            }
         }
     }
 
@@ -365,10 +416,18 @@ constexpr int      kBlockSmall    = 256;
 #define RT_BLOCK_LARGE 1024
 #endif
 constexpr int      kBlockLarge    = RT_BLOCK_LARGE;
+constexpr int      kBlockLarge2   = RT_BLOCK_LARGE / 2;   // two paths per lane: half the threads, twice the registers
 constexpr size_t   kLargeSmemFrom = 56 * 1024;   // above this, < 4 CTAs of 256 threads would fit
 constexpr uint32_t kFilterFrom    = RT_FILTER_FROM;   // spheres from which the kernels filter first
 
-struct RenderVariant { bool smem; int block; int sph; bool tris; size_t hot_bytes; };
+struct RenderVariant { bool smem; int block; int sph; bool tris; size_t hot_bytes; int np; };
+
+// Paths per lane of the FILTER kernels (RT_PATHS_PER_LANE=1 keeps one, for A/B measurements).
+inline int filter_paths_per_lane()
+{
+    static const int np = [] { const char* e = getenv("RT_PATHS_PER_LANE"); return (e && *e == '1') ? 1 : 2; }();
+    return np;
+}
 
 template <bool FAST>
 inline RenderVariant choose_variant(const RtSceneView& G, size_t smem_limit, bool cull)
@@ -378,31 +437,40 @@ inline RenderVariant choose_variant(const RtSceneView& G, size_t smem_limit, boo
     v.tris      = G.n_tri_pad > 0;
     v.hot_bytes = rt_hot_bytes(G, v.sph);
     v.smem      = v.hot_bytes <= smem_limit;
-    v.block     = (v.smem && v.hot_bytes > kLargeSmemFrom) ? kBlockLarge : kBlockSmall;
+    v.np        = v.sph == RT_SPH_FILTER ? filter_paths_per_lane() : 1;
+    v.block     = (v.smem && v.hot_bytes > kLargeSmemFrom) ? (v.np == 2 ? kBlockLarge2 : kBlockLarge) : kBlockSmall;
     return v;
 }
 
 // f(kernel pointer, block) for the variant's instantiation.  Large sphere lists get the FILTER
 // (or, on request, CULL) kernels; worlds without triangles get kernels without the triangle code.
-template <bool FAST, bool SMEM, int BLOCK, int SPH, class F>
+template <bool FAST, bool SMEM, int BLOCK, int SPH, int NP, class F>
 cudaError_t with_kernel4(const RenderVariant& v, F&& f)
 {
-    return v.tris ? f(rt_render_kernel<FAST, SMEM, BLOCK, SPH, true>, BLOCK)
-                  : f(rt_render_kernel<FAST, SMEM, BLOCK, SPH, false>, BLOCK);
-}
-template <bool FAST, bool SMEM, int BLOCK, class F>
-cudaError_t with_kernel3(const RenderVariant& v, F&& f)
-{
-    if (v.sph == RT_SPH_CULL) return with_kernel4<FAST, SMEM, BLOCK, RT_SPH_CULL>(v, f);
-    if (v.sph == RT_SPH_FILTER) return with_kernel4<FAST, SMEM, BLOCK, RT_SPH_FILTER>(v, f);
-    return with_kernel4<FAST, SMEM, BLOCK, RT_SPH_DIRECT>(v, f);
+    return v.tris ? f(rt_render_kernel<FAST, SMEM, BLOCK, SPH, true, NP>, BLOCK)
+                  : f(rt_render_kernel<FAST, SMEM, BLOCK, SPH, false, NP>, BLOCK);
 }
 template <bool FAST, class F>
 cudaError_t with_kernel(const RenderVariant& v, F&& f)
 {
-    if (!v.smem) return with_kernel3<FAST, false, kBlockSmall>(v, f);
-    if (v.block == kBlockLarge) return with_kernel3<FAST, true, kBlockLarge>(v, f);
-    return with_kernel3<FAST, true, kBlockSmall>(v, f);
+    if (v.np == 2) {                                   // FILTER walk, two paths per lane
+        if (!v.smem) return with_kernel4<FAST, false, kBlockSmall, RT_SPH_FILTER, 2>(v, f);
+        if (v.block == kBlockLarge2) return with_kernel4<FAST, true, kBlockLarge2, RT_SPH_FILTER, 2>(v, f);
+        return with_kernel4<FAST, true, kBlockSmall, RT_SPH_FILTER, 2>(v, f);
+    }
+    if (v.sph == RT_SPH_CULL) {
+        if (!v.smem) return with_kernel4<FAST, false, kBlockSmall, RT_SPH_CULL, 1>(v, f);
+        if (v.block == kBlockLarge) return with_kernel4<FAST, true, kBlockLarge, RT_SPH_CULL, 1>(v, f);
+        return with_kernel4<FAST, true, kBlockSmall, RT_SPH_CULL, 1>(v, f);
+    }
+    if (v.sph == RT_SPH_FILTER) {
+        if (!v.smem) return with_kernel4<FAST, false, kBlockSmall, RT_SPH_FILTER, 1>(v, f);
+        if (v.block == kBlockLarge) return with_kernel4<FAST, true, kBlockLarge, RT_SPH_FILTER, 1>(v, f);
+        return with_kernel4<FAST, true, kBlockSmall, RT_SPH_FILTER, 1>(v, f);
+    }
+    if (!v.smem) return with_kernel4<FAST, false, kBlockSmall, RT_SPH_DIRECT, 1>(v, f);
+    if (v.block == kBlockLarge) return with_kernel4<FAST, true, kBlockLarge, RT_SPH_DIRECT, 1>(v, f);
+    return with_kernel4<FAST, true, kBlockSmall, RT_SPH_DIRECT, 1>(v, f);
 }
 
 // Host-side launcher for one policy.
@@ -427,7 +495,7 @@ cudaError_t render_occupancy(const RtSceneView& G, size_t smem_limit, bool cull,
                              size_t* hot_bytes, int* resident, int* sph_mode)
 {
     const RenderVariant v = choose_variant<FAST>(G, smem_limit, cull);
-    *block_size = v.block; *hot_bytes = v.hot_bytes; *resident = v.smem ? 1 : 0; *sph_mode = v.sph;
+    *block_size = v.block; *hot_bytes = v.hot_bytes; *resident = v.smem ? 1 : 0; *sph_mode = v.sph | (v.np << 8);   // walk in bits 0-7, paths per lane above
     return with_kernel<FAST>(v, [&](auto k, int block) -> cudaError_t {
         if (v.smem) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);

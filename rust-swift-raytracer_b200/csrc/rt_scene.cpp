@@ -711,35 +711,76 @@ ParseResult parse_input(const char* source, size_t length, bool allow_emission)
 
 // ------------------------------------------------------------------ image.rs
 
-bool write_image(const Framebuffer& fb, const char* path)   // image.rs:59-81 (ASCII P3)
+// image.rs:59-81 (ASCII P3): "P3\n{w} {h}\n255\n" then one "{r} {g} {b}\n" line per pixel, byte for byte what the
+// reference's write!() calls produce.  The fast path: every channel value has a precomputed "ddd " token
+// (256 x 4 bytes + its length), pixels are formatted straight into a 1 MiB buffer — no per-pixel printf.
+bool write_image(const ColorU8* pixels, size_t width, size_t height, const char* path)
 {
     FILE* f = path ? std::fopen(path, "w") : stdout;
     if (!f) return false;
-    std::string buf;
-    buf.reserve(fb.pixels.size() * 12 + 32);
-    char line[64];
-    int  n = std::snprintf(line, sizeof line, "P3\n%zu %zu\n%d\n", fb.width, fb.height, 255);
-    buf.append(line, (size_t)n);
-    for (const ColorU8& c : fb.pixels) {
-        n = std::snprintf(line, sizeof line, "%u %u %u\n", c.r, c.g, c.b);
-        buf.append(line, (size_t)n);
+    static const struct Tokens {
+        char text[256][4]; unsigned char len[256];
+        Tokens()
+        {
+            for (int v = 0; v < 256; ++v) {
+                int n = 0;
+                if (v >= 100) text[v][n++] = (char)('0' + v / 100);
+                if (v >= 10) text[v][n++] = (char)('0' + (v / 10) % 10);
+                text[v][n++] = (char)('0' + v % 10);
+                len[v] = (unsigned char)n;
+            }
+        }
+    } T;
+    char head[64];
+    const int hn = std::snprintf(head, sizeof head, "P3\n%zu %zu\n%d\n", width, height, 255);
+    bool ok = std::fwrite(head, 1, (size_t)hn, f) == (size_t)hn;
+    constexpr size_t kBuf = (size_t)1 << 20;
+    std::vector<char> buf(kBuf + 16);
+    size_t n = 0;
+    auto put = [&](unsigned v, char sep) {
+        const unsigned l = T.len[v];
+        std::memcpy(&buf[n], T.text[v], 4);      // always 4 bytes: the tail is overwritten by what follows
+        n += l;
+        buf[n++] = sep;
+    };
+    for (size_t i = 0, count = width * height; i < count; ++i) {
+        const ColorU8 c = pixels[i];
+        put(c.r, ' '); put(c.g, ' '); put(c.b, '\n');
+        if (n >= kBuf - 16) { ok = (std::fwrite(buf.data(), 1, n, f) == n) && ok; n = 0; }
     }
-    bool ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    if (n) ok = (std::fwrite(buf.data(), 1, n, f) == n) && ok;
     if (path) ok = (std::fclose(f) == 0) && ok;
     return ok;
 }
 
-bool write_image_p6(const Framebuffer& fb, const char* path)
+// Binary PPM (P6): the same header with the magic P6, then 3 bytes per pixel.
+bool write_image_p6(const ColorU8* pixels, size_t width, size_t height, const char* path)
 {
     FILE* f = std::fopen(path, "wb");
     if (!f) return false;
-    std::fprintf(f, "P6\n%zu %zu\n255\n", fb.width, fb.height);
-    std::vector<unsigned char> rgb(fb.pixels.size() * 3);
-    for (size_t i = 0; i < fb.pixels.size(); ++i) {
-        rgb[3 * i + 0] = fb.pixels[i].r; rgb[3 * i + 1] = fb.pixels[i].g; rgb[3 * i + 2] = fb.pixels[i].b;
+    std::fprintf(f, "P6\n%zu %zu\n255\n", width, height);
+    const size_t count = width * height;
+    constexpr size_t kPix = (size_t)1 << 18;
+    std::vector<unsigned char> rgb(kPix * 3);
+    bool ok = true;
+    for (size_t i0 = 0; i0 < count; i0 += kPix) {
+        const size_t cnt = std::min(kPix, count - i0);
+        for (size_t i = 0; i < cnt; ++i) {
+            const ColorU8 c = pixels[i0 + i];
+            rgb[3 * i + 0] = c.r; rgb[3 * i + 1] = c.g; rgb[3 * i + 2] = c.b;
+        }
+        ok = (std::fwrite(rgb.data(), 1, cnt * 3, f) == cnt * 3) && ok;
     }
-    bool ok = std::fwrite(rgb.data(), 1, rgb.size(), f) == rgb.size();
     return (std::fclose(f) == 0) && ok;
+}
+
+bool write_image(const Framebuffer& fb, const char* path)
+{
+    return fb.pixels.size() == fb.width * fb.height && write_image(fb.pixels.data(), fb.width, fb.height, path);
+}
+bool write_image_p6(const Framebuffer& fb, const char* path)
+{
+    return fb.pixels.size() == fb.width * fb.height && write_image_p6(fb.pixels.data(), fb.width, fb.height, path);
 }
 
 uint32_t shard_tile_count(uint32_t height, uint32_t tile_rows, uint32_t index, uint32_t count)

@@ -30,7 +30,7 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
 
     RtFrameParams P{};
     std::memcpy(&P.camera, cam12, sizeof(float) * 12);
-    P.width = W; P.height = H; P.spp = spp; P.depth = depth; P.seed = seed; P.flags = flags & 0x3fffffffu;   // bits 31/30 select the sphere-walk variant (below)
+    P.width = W; P.height = H; P.spp = spp; P.depth = depth; P.seed = seed; P.flags = flags & 0x1fffffffu;   // bits 31/30/29 select the sphere-walk variant (below)
     P.wm1 = (float)(W - 1u); P.hm1 = (float)(H - 1u);
     P.sample_begin = sample_begin;
     P.resolve_spp  = resolve_spp ? resolve_spp : sample_begin + spp;
@@ -40,6 +40,42 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
     uint64_t rays = 0;
     uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
     const bool trace = spp > 0 && depth > 0;
+    if (flags & 0x20000000u) {
+        // the kernel's NP = 2 loop (rt_kernels.cuh step 2): a lane carries two pixels and walks the lists once
+        // for both rays; when one pixel is complete its path idles with a NaN direction
+        const uint32_t n_px = W * H;
+        for (uint32_t i = 0; i < n_px; i += 2) {
+            Lane L[2] = {};
+            bool have[2];
+            for (int p = 0; p < 2; ++p) {
+                const uint32_t idx = i + (uint32_t)p;
+                have[p] = idx < n_px;
+                if (have[p]) begin_pixel(L[p], P, idx % W, H - 1u - idx / W, idx);
+            }
+            for (;;) {
+                V3   o[2], d[2];
+                Hit  h[2];
+                bool live[2];
+                for (int p = 0; p < 2; ++p) {
+                    live[p] = have[p] && trace && L[p].sample < spp;
+                    o[p] = mk(0.f, 0.f, 0.f);
+                    d[p] = mk(NAN, NAN, NAN);
+                    if (live[p]) { d[p] = segment_begin<false>(L[p], P); o[p] = L[p].o; ++rays; }
+                }
+                if (!live[0] && !live[1]) break;
+                if (G.n_tri_pad) closest_hit_n<false, true, 2>(G.sph_filter, G.sph_r2, G.n_sph, G.n_sph_pad, G.tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, h);
+                else             closest_hit_n<false, false, 2>(G.sph_filter, G.sph_r2, G.n_sph, G.n_sph_pad, G.tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, h);
+                for (int p = 0; p < 2; ++p)
+                    if (live[p]) segment_end<false, RT_SPH_FILTER, true>(L[p], G, G.sph_filter, d[p], h[p]);
+            }
+            for (int p = 0; p < 2; ++p)
+                if (have[p])
+                    out32[L[p].out_index] = resolve_pixel<false>(L[p].acc_r, L[p].acc_g, L[p].acc_b,
+                                                                 pixel_alpha(1.0f, spp > 0 ? spp : 0), P.resolve_spp);
+        }
+        if (rays_out) *rays_out = rays;
+        return 0;
+    }
     for (uint32_t image_row = 0; image_row < H; ++image_row)
         for (uint32_t column = 0; column < W; ++column) {
             Lane L{};

@@ -37,7 +37,7 @@ def test_reference_struct_layouts(rt):
     assert C.sizeof(rt._WorldHandle) == 16 and rt._WorldHandle.camera.offset == 8
     assert rt.lib().rt_abi_version() == 2
     # the Python mirrors of the additive structs are the header's layouts (ABI version 2)
-    assert C.sizeof(rt.RenderStats) == 72 and C.sizeof(rt._RenderOptions) == 72 and C.sizeof(rt.PeerQueue) == 16
+    assert C.sizeof(rt.RenderStats) == 80 and C.sizeof(rt._RenderOptions) == 72 and C.sizeof(rt.PeerQueue) == 16
 
 
 def test_reference_header_is_source_compatible(tmp_path):
@@ -150,3 +150,24 @@ def test_write_image_p3(rt, tmp_path):
     rt.write_image(fb, tmp_path / "b.ppm", binary=True)
     raw = (tmp_path / "b.ppm").read_bytes()
     assert raw.startswith(b"P6\n3 2\n255\n") and raw[-18:] == fb.pixels[:, :, :3].tobytes()
+
+
+def test_write_image_equals_the_oracle_writer_byte_for_byte(rt, ob, tmp_path):
+    """image.rs:59-81: the table-driven P3 writer produces exactly the bytes of the oracle's fprintf restatement —
+    every channel value 0..255 in every position, sizes that straddle the 1 MiB output buffer — and the binary P6
+    file carries the same pixels."""
+    rng = np.random.default_rng(7)
+    for W, H in ((16, 16), (257, 3), (701, 523)):
+        fb = rt.Framebuffer(W, H)
+        fb.pixels[...] = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+        if (W, H) == (16, 16):
+            fb.pixels[:, :, 0] = np.arange(256, dtype=np.uint8).reshape(16, 16)
+            fb.pixels[:, :, 1] = np.arange(256, dtype=np.uint8).reshape(16, 16)[::-1]
+            fb.pixels[:, :, 2] = np.arange(256, dtype=np.uint8).reshape(16, 16).T
+        rt.write_image(fb, tmp_path / "got.ppm")
+        ob.write_image(fb.pixels, str(tmp_path / "want.ppm"))
+        assert (tmp_path / "got.ppm").read_bytes() == (tmp_path / "want.ppm").read_bytes()
+        rt.write_image(fb, tmp_path / "got6.ppm", binary=True)
+        raw = (tmp_path / "got6.ppm").read_bytes()
+        head = b"P6\n%d %d\n255\n" % (W, H)
+        assert raw.startswith(head) and raw[len(head):] == fb.pixels[:, :, :3].tobytes()

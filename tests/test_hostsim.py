@@ -83,6 +83,14 @@ def test_filter_variant_of_the_exact_policy_equals_oracle(hostsim, ob, scenes, k
                                 spp, depth, ob.SEED_DEFAULT, 0x80000000, 0, 0, out.ctypes.data, C.byref(n))
     assert rc == 0 and n.value == rays
     assert np.array_equal(out, want)
+    # two paths per lane (closest_hit_n: both rays against every sphere / plane the lane loads), odd pixel count too
+    for w2, h2 in ((W, H), (W - 1, H - 1)):
+        want2, rays2, _ = ob.ray_trace(world, cam, w2, h2, spp, depth)
+        out = np.zeros((h2, w2, 4), np.uint8)
+        rc = hostsim.hostsim_render(cases.scene_text(scenes, key).encode(), cf.ctypes.data_as(C.POINTER(C.c_float)), w2, h2,
+                                    spp, depth, ob.SEED_DEFAULT, 0x20000000, 0, 0, out.ctypes.data, C.byref(n))
+        assert rc == 0 and n.value == rays2
+        assert np.array_equal(out, want2)
 
 
 @pytest.mark.parametrize("seed", range(12))
@@ -96,7 +104,7 @@ def test_random_worlds_through_the_filters(hostsim, ob, seed):
     W, H, spp, depth = 40, 28, 2, 6
     want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
     cf = cam.floats()
-    for flags in (0, 0x80000000, 0x40000000):         # direct loops, FILTER variant, CULL variant
+    for flags in (0, 0x80000000, 0x40000000, 0x20000000):   # direct loops, FILTER, CULL, FILTER with two paths per lane
         out = np.zeros((H, W, 4), np.uint8)
         n = C.c_uint64()
         rc = hostsim.hostsim_render(text.encode(), cf.ctypes.data_as(C.POINTER(C.c_float)), W, H, spp, depth,
