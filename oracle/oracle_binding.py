@@ -58,7 +58,7 @@ class Options(C.Structure):
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (building the checker is not using it)."""
-    src_m = max((_HERE / n).stat().st_mtime for n in ("rt_oracle.c", "rt_oracle.h", "Makefile"))
+    src_m = max((_HERE / n).stat().st_mtime for n in ("rt_oracle.c", "rt_oracle.h", "unicode_alnum.h", "Makefile"))
     if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src_m:
         subprocess.run(["make", "-C", str(_HERE)], check=True, capture_output=True)
     return _LIB_PATH

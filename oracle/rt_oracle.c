@@ -12,6 +12,7 @@
  */
 #define _GNU_SOURCE
 #include "rt_oracle.h"
+#include "unicode_alnum.h"
 
 #include <locale.h>
 #include <math.h>
@@ -704,15 +705,21 @@ static str skip_whitespace(str s)
     return s;
 }
 
-/* parser.rs:59-62.  DIVERGENCE (documented in DESIGN.md): the reference uses Unicode
- * char::is_alphanumeric; this restatement accepts ASCII [A-Za-z0-9_] only. */
+/* parser.rs:59-62: the longest prefix of chars for which char::is_alphanumeric() holds (Unicode
+ * Alphabetic or general category N*, table in unicode_alnum.h) or that are '_'. */
 static str get_identifier(str s, str *name)
 {
     size_t i = 0;
     while (i < s.n) {
         unsigned char c = (unsigned char)s.p[i];
-        if ((c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_') ++i;
-        else break;
+        if (c < 0x80) {
+            if ((c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_') { ++i; continue; }
+            break;
+        }
+        uint32_t cp;
+        size_t   len = utf8_decode(s.p + i, s.n - i, &cp);
+        if (!rt_is_unicode_alnum(cp)) break;
+        i += len;
     }
     name->p = s.p; name->n = i;
     s.p += i; s.n -= i;

@@ -5,6 +5,7 @@
 // Compiled with -ffp-contract=off: every value computed here (camera vectors, r*r, triangle
 // normals, plane constants) must carry exactly the bits the reference's Rust code computes.
 #include "rt_host.hpp"
+#include "rt_unicode_alnum.h"
 
 #include <clocale>
 #include <algorithm>
@@ -367,7 +368,12 @@ const World::Packed& World::packed() const
     for (size_t i = S; i < Sp; ++i) sph[i] = {nan, nan, nan, nan};            // padding: never hit
     for (size_t j = T; j < Tp; ++j) plane[j] = {nan, nan, nan, nan};
     // block B: the conservative filter list of the exact kernel (rt_trace.cuh, sphere_filter_group)
-    auto* sphf = reinterpret_cast<RtFloat4*>(base + p->off_sph_filter);
+    // The filter records {c, w} are computed per sphere (also the input of block C) and stored for the kernels
+    // in PAIRS, two float4 per pair of consecutive spheres: {x0, x1, y0, y1} {z0, z1, -w0, -w1} — the operand
+    // layout of the two-wide FMAs (FFMA2) the filter runs on.  Sp is even (a multiple of 8).
+    std::vector<RtFloat4> sphf_aos(Sp);
+    RtFloat4* sphf = sphf_aos.data();
+    auto* pairs = reinterpret_cast<RtFloat4*>(base + p->off_sph_filter);
     auto* r2   = reinterpret_cast<float*>(base + p->off_sph_r2);
     for (size_t i = 0; i < Sp; ++i) {
         sphf[i] = sph[i];
@@ -379,6 +385,10 @@ const World::Packed& World::packed() const
         float wf = (float)w;
         if ((double)wf > w) wf = std::nextafterf(wf, -INFINITY);
         sphf[i].w = wf;                                            // NaN padding stays NaN
+    }
+    for (size_t i = 0; i + 1 < Sp; i += 2) {
+        pairs[i]     = {sphf[i].x, sphf[i + 1].x, sphf[i].y, sphf[i + 1].y};
+        pairs[i + 1] = {sphf[i].z, sphf[i + 1].z, -sphf[i].w, -sphf[i + 1].w};
     }
     for (size_t j = 0; j < T; ++j) {
         const Triangle& t = triangles[j];
@@ -394,7 +404,7 @@ const World::Packed& World::packed() const
     }
     std::memcpy(base + off_plane_b, plane, Tp * sizeof(RtFloat4));
     std::memcpy(base + off_plane_c, plane, Tp * sizeof(RtFloat4));
-    if (Gc) build_cull_block(order, reinterpret_cast<const RtFloat4*>(base + p->off_sph_filter),
+    if (Gc) build_cull_block(order, sphf,
                              reinterpret_cast<const float*>(base + p->off_sph_r2),
                              reinterpret_cast<RtFloat4*>(base + p->off_cull_bound),
                              reinterpret_cast<RtFloat4*>(base + p->off_cull_sph),
@@ -530,14 +540,19 @@ struct Cursor {
             s.remove_prefix(len);
         }
     }
-    // parser.rs:59-62.  ASCII [A-Za-z0-9_] (the reference accepts Unicode alphanumerics)
+    // parser.rs:59-62: the longest prefix of chars with char::is_alphanumeric() (Unicode Alphabetic or N*) or '_'
     sv identifier()
     {
         size_t i = 0;
         while (i < s.size()) {
-            unsigned char c = (unsigned char)s[i];
-            if ((c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_') ++i;
-            else break;
+            const unsigned char c = (unsigned char)s[i];
+            if (c < 0x80) {
+                if ((c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_') { ++i; continue; }
+                break;
+            }
+            uint32_t cp; const size_t len = decode(s.substr(i), cp);
+            if (!rt_is_unicode_alnum(cp)) break;
+            i += len;
         }
         sv name = s.substr(0, i);
         s.remove_prefix(i);

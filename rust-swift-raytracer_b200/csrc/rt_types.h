@@ -7,7 +7,9 @@
 //   [ sph       : float4 x Sp]  {cx, cy, cz, r*r}                 hot
 //   [ tri_plane : float4 x Tp]  {n.x, n.y, n.z, n.v0}             hot
 //   block B (staged instead of A by the FILTER kernels, large sphere counts)
-//   [ sph_filter: float4 x Sp]  {cx, cy, cz, c.c - r*r - margin}  hot  (rt_trace.cuh, sphere_filter_group)
+//   [ sph_filter: float4 x Sp]  the filter records {cx, cy, cz, w = c.c - r*r - margin} of consecutive spheres in
+//                               PAIRS, two float4 per pair: {x0, x1, y0, y1} {z0, z1, -w0, -w1} — the operand layout of
+//                               the two-wide FMAs (FFMA2)                   hot  (rt_trace.cuh, sphere_filter_group_n)
 //   [ tri_plane : float4 x Tp]  (same as in block A)              hot
 //   [ sph_r2    : float  x Sp]  r*r                               warm (filter survivors only)
 //   block C (staged instead of A/B by the CULL kernels: RT_FLAG_GROUP_CULL, an opt-in mode)

@@ -126,7 +126,12 @@ extern "C" int hostsim_check_cull(const char* scene_text, uint32_t* n_groups_out
             if (idx == 0xffffffffu) { if (s.x == s.x) return 103; continue; }      // padding must be NaN
             if (idx >= G.n_sph) return 104;
             ++seen[idx];
-            if (std::memcmp(&s, &G.sph_filter[idx], sizeof s) != 0) return 105;
+            {   // block B stores the same records in pairs: {x0, x1, y0, y1} {z0, z1, -w0, -w1}
+                const float* f = reinterpret_cast<const float*>(G.sph_filter + (idx & ~1u));
+                const uint32_t h = idx & 1u;
+                const RtFloat4 rec = {f[h], f[2 + h], f[4 + h], -f[6 + h]};
+                if (std::memcmp(&s, &rec, sizeof s) != 0) return 105;
+            }
             if (std::memcmp(&G.cull_r2[8u * g + k], &G.sph_r2[idx], sizeof(float)) != 0) return 106;
             if (pass_always) continue;
             const double c[3] = {s.x, s.y, s.z}, r = std::sqrt((double)G.sph_r2[idx]);
