@@ -422,10 +422,13 @@ constexpr uint32_t kFilterFrom    = RT_FILTER_FROM;   // spheres from which the 
 
 struct RenderVariant { bool smem; int block; int sph; bool tris; size_t hot_bytes; int np; };
 
-// Paths per lane of the FILTER kernels (RT_PATHS_PER_LANE=1 keeps one, for A/B measurements).
+// Paths per lane of the FILTER kernels.  Measured with the FFMA2 filter (profiles/r02_bench.md): one path per lane
+// is as fast as two on C3 exact (302 vs 304 ms), 3 % slower on C3 fast-math (290 vs 281 ms) and 17 % FASTER on C5
+// (194 vs 233 ms: sixteen warps per SM do not hide the latencies of its long, divergent paths), so one is the
+// default; RT_PATHS_PER_LANE=2 selects the two-path kernels.
 inline int filter_paths_per_lane()
 {
-    static const int np = [] { const char* e = getenv("RT_PATHS_PER_LANE"); return (e && *e == '1') ? 1 : 2; }();
+    static const int np = [] { const char* e = getenv("RT_PATHS_PER_LANE"); return (e && *e == '2') ? 2 : 1; }();
     return np;
 }
 

@@ -348,7 +348,7 @@ const World::Packed& World::packed() const
     const size_t off_plane_c = off; off += Tp * sizeof(RtFloat4);
     p->off_cull_r2    = off; off += align_up(8 * Gc * sizeof(float), 16);
     p->off_cull_orig  = off; off += align_up(8 * Gc * sizeof(uint32_t), 16);
-    p->off_tri_cull  = off; off += 3 * T * sizeof(RtFloat4);
+    p->off_tri_cull  = off; off += 5 * (Tp / 2) * sizeof(RtFloat4);
     p->off_tri_v     = off; off += 3 * T * sizeof(RtFloat4);
     off = align_up(off, 32);
     p->off_info      = off; off += P * sizeof(RtPrimInfo);
@@ -366,7 +366,10 @@ const World::Packed& World::packed() const
     }
     const float nan = std::nanf("");
     for (size_t i = S; i < Sp; ++i) sph[i] = {nan, nan, nan, nan};            // padding: never hit
-    for (size_t j = T; j < Tp; ++j) plane[j] = {nan, nan, nan, nan};
+    std::vector<RtFloat4> sph_aos(sph, sph + Sp);                             // {c, r*r} per sphere, for the lists below
+    std::vector<RtFloat4> plane_aos(Tp, RtFloat4{nan, nan, nan, nan});       // {n, n.v0} per triangle; NaN padding
+    std::vector<RtFloat4> cull_aos(3 * Tp, RtFloat4{0.f, 0.f, 0.f, 0.f});
+    for (size_t j = T; j < Tp; ++j) cull_aos[3 * j + 2].x = -INFINITY;        // padding: never culled, never hit (NaN plane)
     // block B: the conservative filter list of the exact kernel (rt_trace.cuh, sphere_filter_group)
     // The filter records {c, w} are computed per sphere (also the input of block C) and stored for the kernels
     // in PAIRS, two float4 per pair of consecutive spheres: {x0, x1, y0, y1} {z0, z1, -w0, -w1} — the operand
@@ -376,11 +379,12 @@ const World::Packed& World::packed() const
     auto* pairs = reinterpret_cast<RtFloat4*>(base + p->off_sph_filter);
     auto* r2   = reinterpret_cast<float*>(base + p->off_sph_r2);
     for (size_t i = 0; i < Sp; ++i) {
-        sphf[i] = sph[i];
-        r2[i]   = sph[i].w;
+        const RtFloat4 si = sph_aos[i];
+        sphf[i] = si;
+        r2[i]   = si.w;
         // w = c.c - r^2 - 2^-17 (c.c + r^2), in double, rounded DOWN (a smaller w only lets more spheres through)
-        const double cc = (double)sph[i].x * sph[i].x + (double)sph[i].y * sph[i].y + (double)sph[i].z * sph[i].z;
-        const double rr = (double)sph[i].w;
+        const double cc = (double)si.x * si.x + (double)si.y * si.y + (double)si.z * si.z;
+        const double rr = (double)si.w;
         const double w  = cc - rr - (cc + rr) * (1.0 / 131072.0) - 1e-30;
         float wf = (float)w;
         if ((double)wf > w) wf = std::nextafterf(wf, -INFINITY);
@@ -389,18 +393,35 @@ const World::Packed& World::packed() const
     for (size_t i = 0; i + 1 < Sp; i += 2) {
         pairs[i]     = {sphf[i].x, sphf[i + 1].x, sphf[i].y, sphf[i + 1].y};
         pairs[i + 1] = {sphf[i].z, sphf[i + 1].z, -sphf[i].w, -sphf[i + 1].w};
+        // block A, the direct kernels' list, in the same pair layout with r*r in the last slots
+        sph[i]       = {sph_aos[i].x, sph_aos[i + 1].x, sph_aos[i].y, sph_aos[i + 1].y};
+        sph[i + 1]   = {sph_aos[i].z, sph_aos[i + 1].z, sph_aos[i].w, sph_aos[i + 1].w};
     }
     for (size_t j = 0; j < T; ++j) {
         const Triangle& t = triangles[j];
         // common.rs:128-133,140: n = (v1-v0) x (v2-v0) and d = n.v0 depend on the triangle
         // only, so they are evaluated once here with the reference's exact operation order.
         const F3 n = cross3(sub(f3(t.v1), f3(t.v0)), sub(f3(t.v2), f3(t.v0)));
-        plane[j]        = {n.x, n.y, n.z, dot3(n, f3(t.v0))};
+        plane_aos[j]    = {n.x, n.y, n.z, dot3(n, f3(t.v0))};
         triv[3 * j + 0] = {t.v0.x, t.v0.y, t.v0.z, t.normal.x};
         triv[3 * j + 1] = {t.v1.x, t.v1.y, t.v1.z, t.normal.y};
         triv[3 * j + 2] = {t.v2.x, t.v2.y, t.v2.z, t.normal.z};
         info[S + j]     = prim_info(t.material, 1.0f);
-        triangle_cull_record(t, &cull[3 * j]);
+        triangle_cull_record(t, &cull_aos[3 * j]);
+    }
+    // the hot / warm triangle lists in PAIRS of consecutive triangles — the operand layout of the two-wide FP32
+    // instructions of rt_trace.cuh triangle_group_n (Tp is even; the last pair of an odd list ends in the padding)
+    for (size_t j = 0; j + 1 < Tp; j += 2) {
+        const RtFloat4 a = plane_aos[j], b = plane_aos[j + 1];
+        plane[j]     = {a.x, b.x, a.y, b.y};
+        plane[j + 1] = {a.z, b.z, a.w, b.w};
+        const RtFloat4 *ca = &cull_aos[3 * j], *cb = &cull_aos[3 * (j + 1)];
+        RtFloat4* q = &cull[5 * (j / 2)];
+        q[0] = {ca[0].x, cb[0].x, ca[0].y, cb[0].y};
+        q[1] = {ca[0].z, cb[0].z, ca[0].w, cb[0].w};
+        q[2] = {ca[1].x, cb[1].x, ca[1].y, cb[1].y};
+        q[3] = {ca[1].z, cb[1].z, ca[1].w, cb[1].w};
+        q[4] = {ca[2].x, cb[2].x, 0.f, 0.f};
     }
     std::memcpy(base + off_plane_b, plane, Tp * sizeof(RtFloat4));
     std::memcpy(base + off_plane_c, plane, Tp * sizeof(RtFloat4));

@@ -4,8 +4,10 @@
 // load_world / World::new and never touched by the render loop again):
 //
 //   block A (staged into shared memory by the direct kernels)
-//   [ sph       : float4 x Sp]  {cx, cy, cz, r*r}                 hot
-//   [ tri_plane : float4 x Tp]  {n.x, n.y, n.z, n.v0}             hot
+//   [ sph       : float4 x Sp]  {cx, cy, cz, r*r} of consecutive spheres in PAIRS, two float4 per pair:
+//                               {x0, x1, y0, y1} {z0, z1, r0*r0, r1*r1} (operands of FMUL2 / FADD2)          hot
+//   [ tri_plane : float4 x Tp]  {n.x, n.y, n.z, n.v0} of consecutive triangles in PAIRS: {nx0, nx1, ny0, ny1}
+//                               {nz0, nz1, w0, w1}                                                          hot
 //   block B (staged instead of A by the FILTER kernels, large sphere counts)
 //   [ sph_filter: float4 x Sp]  the filter records {cx, cy, cz, w = c.c - r*r - margin} of consecutive spheres in
 //                               PAIRS, two float4 per pair: {x0, x1, y0, y1} {z0, z1, -w0, -w1} — the operand layout of
@@ -21,8 +23,9 @@
 //   [ cull_r2   : float  x 8Gc] r*r in the same order                                 warm
 //   [ cull_orig : u32    x 8Gc] list index of each sphere (hit-test order = tie-break order)  warm
 //   then
-//   [ tri_cull  : float4 x 3T]  {G2.xyz, g2}, {G0.xyz, g0}, {K,0,0,0}: approximate barycentric
-//                               gradients for the conservative edge-stage reject   warm (plane-stage survivors)
+//   [ tri_cull  : float4 x 5Tp/2]  per PAIR of triangles {G2.xyz, g2}, {G0.xyz, g0}, K — approximate barycentric
+//                               gradients for the conservative edge-stage reject — as {G2x0,G2x1,G2y0,G2y1}
+//                               {G2z0,G2z1,g2_0,g2_1} {G0x0,..} {G0z0,..,g0_1} {K0,K1,0,0}   warm (plane-stage survivors)
 //   [ tri_v     : float4 x 3T]  {v_k.xyz, stored_normal[k]}       cool (reject survivors)
 //   [ info      : 32 B   x P ]  RtPrimInfo                        cold (one gather per hit), P = S+T
 //

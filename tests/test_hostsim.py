@@ -13,16 +13,26 @@ import cases
 HERE = Path(__file__).resolve().parent
 
 
-@pytest.fixture(scope="module")
-def hostsim():
+def _load(name):
     subprocess.run(["make", "-C", str(HERE / "hostsim")], check=True, capture_output=True)
-    L = C.CDLL(str(HERE / "hostsim" / "build" / "libhostsim.so"))
+    L = C.CDLL(str(HERE / "hostsim" / "build" / name))
     L.hostsim_render.restype = C.c_int
     L.hostsim_render.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.c_int32, C.c_int32,
                                  C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64)]
     L.hostsim_check_cull.restype = C.c_int
     L.hostsim_check_cull.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     return L
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    return _load("libhostsim.so")
+
+
+@pytest.fixture(scope="module")
+def hostsim_perturbed():
+    """The same build with rcp_approx (MUFU.RCP on the device) moved one ulp up or down pseudo-randomly."""
+    return _load("libhostsim_perturb.so")
 
 
 def test_cull_block_invariants(hostsim, scenes):
@@ -126,3 +136,35 @@ def test_degenerate_frames(hostsim, ob, scenes, W, H, spp, depth):
                                 depth, ob.SEED_DEFAULT, 0, 0, spp, out.ctypes.data, C.byref(n))
     assert rc == 0 and n.value == rays
     assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("seed", range(40, 70))
+def test_random_worlds_with_perturbed_reciprocals(hostsim_perturbed, ob, seed):
+    """The conservative triangle filters (approximate quotient ta = num * rcp.approx(den), window margin 2^-19, edge
+    reject on p(ta)) must not depend on the last bits of the approximation: with every rcp_approx result moved one
+    ulp up or down, frames and ray counts still equal the oracle's — on awkward geometry, all sphere walks."""
+    text = cases.random_world(seed, n_spheres=66, n_triangles=40)
+    cam, world = ob.parse_input(text)
+    W, H, spp, depth = 36, 24, 2, 6
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    cf = cam.floats()
+    for flags in (0, 0x80000000, 0x20000000):
+        out = np.zeros((H, W, 4), np.uint8)
+        n = C.c_uint64()
+        rc = hostsim_perturbed.hostsim_render(text.encode(), cf.ctypes.data_as(C.POINTER(C.c_float)), W, H, spp, depth,
+                                              ob.SEED_DEFAULT, flags, 0, 0, out.ctypes.data, C.byref(n))
+        assert rc == 0 and n.value == rays, (seed, flags)
+        assert np.array_equal(out, want), (seed, flags)
+
+
+def test_c5_triangles_with_perturbed_reciprocals(hostsim_perturbed, ob, scenes):
+    text = scenes.synthetic_world(200, 600, seed=10000)          # triangle-heavy cut of the C5 generator
+    cam, world = ob.parse_input(text)
+    W, H, spp, depth = 48, 27, 2, 16
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    out = np.zeros((H, W, 4), np.uint8)
+    n = C.c_uint64()
+    cf = cam.floats()
+    rc = hostsim_perturbed.hostsim_render(text.encode(), cf.ctypes.data_as(C.POINTER(C.c_float)), W, H, spp, depth,
+                                          ob.SEED_DEFAULT, 0x80000000, 0, 0, out.ctypes.data, C.byref(n))
+    assert rc == 0 and n.value == rays and np.array_equal(out, want)

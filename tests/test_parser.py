@@ -20,7 +20,19 @@ VALID = [
     "camera origin 0.0 0.0 0.0 aspect 1.0;\nmaterial  : Diffuse color 1.0 0.0 0.0;\nsphere center 0.0 0.0 -1.0 radius 0.5 material ;\n",  # empty name
 ]
 
+# parser.rs:59-62: material names are runs of char::is_alphanumeric() (UNICODE Alphabetic / Numeric) or '_'
+VALID += [
+    "camera origin 0.0 0.0 0.0 aspect 1.0;\nmaterial RÖD_färg : Diffuse color 1.0 0.0 0.0;\n"
+    "sphere center 0.0 0.0 -1.0 radius 0.5 material RÖD_färg;\n",                                  # Latin-1 letters
+    "camera origin 0.0 0.0 0.0 aspect 1.0;\nmaterial 金属٣Ⅻ : Metal color 0.5 0.5 0.5 fuzz 0.1;\n"
+    "sphere center 0.0 0.0 -1.0 radius 0.5 material 金属٣Ⅻ;\n",                                     # CJK, Arabic-Indic digit (Nd), Roman numeral (Nl)
+    "camera origin 0.0 0.0 0.0 aspect 1.0;\nmaterial 𝔊𐐷 : Dielectric ir 1.5;\n"
+    "sphere center 0.0 0.0 -1.0 radius 0.5 material 𝔊𐐷;\n",                                        # 4-byte scalars (SMP letters)
+]
+
 INVALID = [
+    "camera origin 0.0 0.0 0.0 aspect 1.0;\nmaterial A→B : Diffuse color 1.0 0.0 0.0;\n",           # U+2192 is not alphanumeric
+    "camera origin 0.0 0.0 0.0 aspect 1.0;\nmaterial A😀 : Diffuse color 1.0 0.0 0.0;\n",           # emoji: So
     "",
     " camera origin 0.0 0.0 0.0 aspect 1.0;",                          # leading whitespace: MissingCamera
     "// c\n\ncamera origin 0.0 0.0 0.0 aspect 1.0;",                   # blank line after comment: MissingCamera
