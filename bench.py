@@ -336,7 +336,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world_size > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=300))    # a failed rank must not stall the run for long
     n_gpus = world_size
     if args.gpus != n_gpus and rank == 0:
         print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world_size}; using {n_gpus}", file=sys.stderr)

@@ -273,6 +273,7 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     P.tile_stride  = opt.shard_count;
     P.n_tiles      = L.n_tiles;
     P.passes       = 1;
+    P.one          = 1.0f;
     P.out          = L.d_out;
     P.accum        = static_cast<RtFloat4*>(device_accum);
     P.ray_counter  = &L.slot->rays;

@@ -323,7 +323,7 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
                 }
             }
             if (live) {
-                closest_hit_n<FAST, TRIS, NP>(sph, sph_r2, G.n_sph, G.n_sph_pad, tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, h);
+                closest_hit_n<FAST, TRIS, NP>(sph, sph_r2, G.n_sph, G.n_sph_pad, tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, P.one, h);
 #pragma unroll
                 for (int p = 0; p < NP; ++p)
                     if (ready[p] && trace) sample_done[p] = segment_end<FAST, SPH, TRIS>(L[p], G, sph, d[p], h[p]);

@@ -167,6 +167,9 @@ struct RtFrameParams {
     // 16-byte record carries its own "ready" tag, and a lane whose pixel is not ready yet simply
     // retries in its next loop iteration.  No drain between passes, one ramp-up per frame.
     uint32_t passes;
+    float    one;            // 1.0f, as a value the compiler cannot see: multiplier of the exact policy's two-wide sums
+                             // (rt_trace.cuh f2_add1) — set by the host, never anything else
+    uint32_t pad_one;
     uint32_t* out;           // RGBA8 as u32, full frame or compact (RT_FLAG_COMPACT_OUT)
     RtFloat4* accum;         // optional float4 sums, same indexing as out
     unsigned long long* ray_counter;   // += number of World::hit calls

@@ -4,8 +4,8 @@ set -u
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
-python -m pytest tests -m gpu -q -k "gpus or per_gpu or stealing or unbalanced or another_device or two_devices or many_gpus" > gpurun_out/pytest_multi.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_multi.log
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N "$@"; }
+timeout 600 python -m pytest tests -m gpu -q -k "gpus or per_gpu or stealing or unbalanced or another_device or two_devices or many_gpus" > gpurun_out/pytest_multi.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_multi.log
+run() { timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N "$@"; }
 run --steps 5 --warmup 3 > gpurun_out/bench_c4_n$N.json 2> gpurun_out/bench_c4_n$N.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_c4_n$N.err
 run --steps 5 --warmup 3 --no-steal --no-extras > gpurun_out/bench_c4_n${N}_nosteal.json 2>> gpurun_out/bench_c4_n$N.err; echo "bench(no steal) rc=$?"
 python - <<PY

@@ -33,6 +33,7 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
     P.width = W; P.height = H; P.spp = spp; P.depth = depth; P.seed = seed; P.flags = flags & 0x1fffffffu;   // bits 31/30/29 select the sphere-walk variant (below)
     P.wm1 = (float)(W - 1u); P.hm1 = (float)(H - 1u);
     P.sample_begin = sample_begin;
+    P.one = 1.0f;
     P.resolve_spp  = resolve_spp ? resolve_spp : sample_begin + spp;
 
     CullView cv{G.cull_bound, G.cull_sph, G.cull_r2, G.cull_orig, G.n_groups};
@@ -63,8 +64,8 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
                     if (live[p]) { d[p] = segment_begin<false>(L[p], P); o[p] = L[p].o; ++rays; }
                 }
                 if (!live[0] && !live[1]) break;
-                if (G.n_tri_pad) closest_hit_n<false, true, 2>(G.sph_filter, G.sph_r2, G.n_sph, G.n_sph_pad, G.tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, h);
-                else             closest_hit_n<false, false, 2>(G.sph_filter, G.sph_r2, G.n_sph, G.n_sph_pad, G.tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, h);
+                if (G.n_tri_pad) closest_hit_n<false, true, 2>(G.sph_filter, G.sph_r2, G.n_sph, G.n_sph_pad, G.tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, P.one, h);
+                else             closest_hit_n<false, false, 2>(G.sph_filter, G.sph_r2, G.n_sph, G.n_sph_pad, G.tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, P.one, h);
                 for (int p = 0; p < 2; ++p)
                     if (live[p]) segment_end<false, RT_SPH_FILTER, true>(L[p], G, G.sph_filter, d[p], h[p]);
             }
