@@ -339,6 +339,9 @@ def main():
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
                                 timeout=datetime.timedelta(seconds=300))    # a failed rank must not stall the run for long
+        # a CPU-side group: while rank 0 measures something alone, the others wait on the HOST — an NCCL barrier
+        # would keep a spinning kernel on their GPUs, which rank 0's one-process leg needs for itself
+        host_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=300))
     n_gpus = world_size
     if args.gpus != n_gpus and rank == 0:
         print(f"# note: --gpus {args.gpus} but WORLD_SIZE={world_size}; using {n_gpus}", file=sys.stderr)
@@ -359,6 +362,11 @@ def main():
         if n_gpus > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if n_gpus > 1:
+            dist.barrier(group=host_group)
 
     def allreduce(x, op):
         if n_gpus == 1:
@@ -466,12 +474,13 @@ def main():
                 extras["ppm"] = {"error": repr(e)}
         else:
             # the SAME frame on one GPU, in this run: the base of the strong-scaling figure and the parity check
+            host_barrier()
             base = None
             if rank == 0:
                 rec, sha1, rays1 = time_workload_1gpu(torch, rt, multi, scenes, args.workload, dev, flush, 2, 3,
                                                       fp32_peak=fp32_peak)
                 base = (rec, sha1, rays1)
-            barrier()
+            host_barrier()
             if rank == 0:
                 rec, sha1, rays1 = base
                 extras["strong_scaling"] = {"base_ms_1gpu": rec["ms_per_step"], "base_value_1gpu": rec["value"],
@@ -503,7 +512,7 @@ def main():
                                "pageable host framebuffer"}
                 except Exception as e:      # noqa: BLE001
                     extras["e2e_one_process"] = {"error": repr(e)}
-            barrier()
+            host_barrier()
 
     one_process = None
     if args.devices > 1 and n_gpus == 1:

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -459,6 +460,29 @@ uint64_t shard_pixels(uint32_t W, uint32_t H, const Options& opt, uint32_t n_til
     return px;
 }
 
+// Staging frame -> the caller's pageable frame.  One core moves ~12 GB/s out of the freshly DMA-written (cache-cold)
+// staging buffer, so large frames are split over a few threads (measured on C2, 8.3 MB: 0.70 -> see profiles/r02_bench.md).
+void copy_frame(void* dst, const void* src, size_t bytes)
+{
+    static const unsigned workers = [] {
+        const char* e = std::getenv("RT_COPY_THREADS");
+        unsigned n = e ? (unsigned)std::atoi(e) : 4u;
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (hw && n > hw) n = hw;
+        return n < 1u ? 1u : n;
+    }();
+    if (workers == 1 || bytes < ((size_t)2 << 20)) { std::memcpy(dst, src, bytes); return; }
+    const size_t piece = ((bytes + workers - 1) / workers + 4095) & ~(size_t)4095;
+    std::vector<std::thread> pool;
+    for (unsigned i = 1; i < workers; ++i) {
+        const size_t off = (size_t)i * piece;
+        if (off >= bytes) break;
+        pool.emplace_back([=] { std::memcpy((char*)dst + off, (const char*)src + off, std::min(piece, bytes - off)); });
+    }
+    std::memcpy(dst, src, std::min(piece, bytes));
+    for (auto& t : pool) t.join();
+}
+
 void ensure_stage(DeviceContext& ctx, size_t bytes)
 {
     if (ctx.h_stage_cap >= bytes) return;
@@ -523,7 +547,7 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
         if (staged_zero_copy) {              // this shard's rows of the staging frame -> the caller's frame
             const size_t tile_px = (size_t)opt.tile_rows * W;
             if (opt.shard_count <= 1) {
-                std::memcpy(host_pixels, ctx.h_stage, (size_t)W * H * 4);
+                copy_frame(host_pixels, ctx.h_stage, (size_t)W * H * 4);
             } else {
                 for (uint32_t j = 0; j < n_tiles; ++j) {
                     const size_t first = (size_t)rt_shard_tile(opt.shard_index, opt.shard_count, j) * tile_px;
@@ -577,7 +601,7 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
         RT_CUDA(cudaStreamSynchronize(stream));
         if (!direct)
             for_each_piece([&](size_t frame_px, size_t dev_px, size_t count) {
-                std::memcpy(host32 + frame_px, ctx.h_stage + dev_px * 4, count * 4);
+                copy_frame(host32 + frame_px, ctx.h_stage + dev_px * 4, count * 4);
             });
         }
     } else if (!user_stream) {
@@ -742,7 +766,7 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
         if (!direct) { ensure_stage(c0, (size_t)W * H * 4); dst = c0.h_stage; }
         RT_CUDA(cudaMemcpyAsync(dst, c0.d_out, (size_t)W * H * 4, cudaMemcpyDeviceToHost, c0.stream));
         RT_CUDA(cudaStreamSynchronize(c0.stream));
-        if (!direct) std::memcpy(host32, c0.h_stage, (size_t)W * H * 4);
+        if (!direct) copy_frame(host32, c0.h_stage, (size_t)W * H * 4);
     }
 
     if (opt_in.stats) {
