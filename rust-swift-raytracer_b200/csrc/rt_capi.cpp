@@ -77,6 +77,8 @@ rt::Options to_options(const RtRenderOptions* o)
     static_assert(sizeof(RtPeerQueue) == sizeof(rt::PeerQueue), "RtPeerQueue mirrors rt::PeerQueue");
     r.peer_queues       = reinterpret_cast<const rt::PeerQueue*>(c.peer_queues);
     r.n_peer_queues     = c.peer_queues ? c.n_peer_queues : 0u;
+    r.no_steal          = (c.flags & RT_OPT_NO_STEAL) != 0;
+    r.tile_gather       = (c.flags & RT_OPT_NO_TILE_GATHER) == 0;
     return r;
 }
 

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -57,6 +58,18 @@ struct CounterSlot {            // 16 B, zeroed by one memset per launch
 // the float4 sums of the fused passes for the full frame.  Lives in its owner's device memory; the
 // other GPUs reach it through peer access or a CUDA-IPC mapping.
 constexpr size_t       kBlockHeader    = 256;
+// layout of a shard block for a width x height frame: [header][tile counters, one per 4-row tile at most][float4 sums]
+// [RGBA8 frame]; the last three are indexed like the full frame
+struct BlockLayout { size_t off_tiles, off_accum, off_frame, bytes; };
+BlockLayout block_layout(size_t W, size_t H)
+{
+    BlockLayout b;
+    b.off_tiles = kBlockHeader;
+    b.off_accum = b.off_tiles + ((((H + 3) / 4) * sizeof(unsigned int) + 255) & ~(size_t)255);
+    b.off_frame = b.off_accum + W * H * sizeof(RtFloat4);
+    b.bytes     = b.off_frame + W * H * sizeof(uint32_t);
+    return b;
+}
 constexpr unsigned int kQueueExhausted = 0xC0000000u;   // any value >= every queue length (< 2^31)
 
 struct DeviceContext {
@@ -74,6 +87,8 @@ struct DeviceContext {
     RtFloat4*    d_samples = nullptr;  size_t d_samples_cap = 0; // per-sample colours of the sample-item mode
     RtFloat4*    d_accum = nullptr;    size_t d_accum_cap = 0;   // hand-over sums between sample-item chunks / fused passes
     unsigned char* d_block = nullptr;  size_t d_block_cap = 0;   // this device's shard block (ray_trace_multi)
+    unsigned int* d_tile_done = nullptr; unsigned int* h_tile_flags = nullptr; size_t tile_cap = 0;   // tile completion
+    uint32_t     tile_epoch = 0;
     struct Geometry { int per_sm = 0, block = 0, resident = 0, sph_mode = 0; size_t hot_bytes = 0; };
     std::map<std::tuple<uint32_t, uint32_t, uint32_t, int, int>, Geometry> occupancy;   // (Sp, Tp, groups, fast, cull) -> launch geometry
 };
@@ -209,6 +224,7 @@ struct ShardLaunch {
     size_t       hot_bytes = 0, smem_limit = 0;
     bool         resident = false, filtered = false, culled = false, sample_items = false;
     uint32_t     launches = 0, passes_fused = 0, paths_per_lane = 1;
+    bool         tile_flags = false;       // the kernel publishes per-tile completion flags (ctx.h_tile_flags, ctx.tile_epoch)
     CounterSlot* slot = nullptr;
     uint32_t*    d_out = nullptr;
 };
@@ -233,7 +249,8 @@ void validate(size_t width, size_t height, const Options& opt, const void* devic
 }
 
 ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Camera& camera, uint32_t W, uint32_t H,
-                          const Options& opt, uint32_t* d_out_in, void* device_accum, cudaStream_t stream, bool timed)
+                          const Options& opt, uint32_t* d_out_in, void* device_accum, cudaStream_t stream, bool timed,
+                          bool want_tile_flags = false)
 {
     ShardLaunch L;
     L.n_tiles = shard_tile_count(H, opt.tile_rows, opt.shard_index, opt.shard_count);
@@ -330,26 +347,40 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
         }
     }
 
-    // Cross-GPU work stealing: the queue table of this launch, own shard first.
-    const bool     stealing  = opt.n_peer_queues > 1 && !L.sample_items && trace;
+    // Cross-GPU work stealing and tile gather: the queue table of this launch, own shard first.
+    const BlockLayout BL = block_layout(W, H);
+    const bool     have_blocks = opt.n_peer_queues > 0 && !L.sample_items && trace;
+    const bool     stealing    = have_blocks && opt.n_peer_queues > 1 && !opt.no_steal;
+    const bool     gathering   = have_blocks && opt.tile_gather && !opt.no_resolve && L.d_out != nullptr;
     unsigned char* own_block = nullptr;
     for (uint32_t i = 0; i < opt.n_peer_queues; ++i)
         if (opt.peer_queues[i].shard_index == opt.shard_index) own_block = static_cast<unsigned char*>(opt.peer_queues[i].block);
     if (opt.n_peer_queues && !own_block) throw std::runtime_error("peer_queues does not contain this shard's own block");
-    if (own_block && !L.sample_items) P.accum = reinterpret_cast<RtFloat4*>(own_block + kBlockHeader);
-    if (stealing) {
+    auto queue_of = [&](unsigned char* b, uint32_t shard) {
+        RtQueue q{};
+        q.work_counter = reinterpret_cast<unsigned int*>(b);
+        q.accum        = reinterpret_cast<RtFloat4*>(b + BL.off_accum);
+        q.tile_done    = reinterpret_cast<unsigned int*>(b + BL.off_tiles);
+        // the shard on the gathering GPU writes its pixels straight into the destination frame
+        q.frame        = (gathering && shard == opt.gather_shard) ? L.d_out : reinterpret_cast<uint32_t*>(b + BL.off_frame);
+        q.tile_first   = shard;
+        q.n_tiles      = shard_tile_count(H, opt.tile_rows, shard, opt.shard_count);
+        return q;
+    };
+    if (have_blocks) {
+        P.accum        = reinterpret_cast<RtFloat4*>(own_block + BL.off_accum);
         P.work_counter = reinterpret_cast<unsigned int*>(own_block);
         uint32_t n = 0;
-        P.queues[n++] = RtQueue{P.work_counter, P.accum, opt.shard_index, L.n_tiles};
-        for (uint32_t i = 0; i < opt.n_peer_queues; ++i) {
-            const PeerQueue& pq = opt.peer_queues[i];
-            if (pq.shard_index == opt.shard_index) continue;
-            if (pq.shard_index >= opt.shard_count || !pq.block) throw std::runtime_error("bad peer queue entry");
-            unsigned char* b = static_cast<unsigned char*>(pq.block);
-            P.queues[n++] = RtQueue{reinterpret_cast<unsigned int*>(b), reinterpret_cast<RtFloat4*>(b + kBlockHeader),
-                                    pq.shard_index, shard_tile_count(H, opt.tile_rows, pq.shard_index, opt.shard_count)};
-        }
+        P.queues[n++] = queue_of(own_block, opt.shard_index);
+        if (stealing)
+            for (uint32_t i = 0; i < opt.n_peer_queues; ++i) {
+                const PeerQueue& pq = opt.peer_queues[i];
+                if (pq.shard_index == opt.shard_index) continue;
+                if (pq.shard_index >= opt.shard_count || !pq.block) throw std::runtime_error("bad peer queue entry");
+                P.queues[n++] = queue_of(static_cast<unsigned char*>(pq.block), pq.shard_index);
+            }
         P.n_queues = n;
+        if (gathering) P.gather_dst = L.d_out;
     }
 
     // Progressive passes fused into this launch (rt_types.h): needs a fresh frame (the alpha sum tags the
@@ -371,12 +402,14 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
             }
             P.accum = ctx.d_accum;
         }
-        if (stealing) P.queues[0].accum = P.accum;
+        if (have_blocks) P.queues[0].accum = P.accum;
         L.passes_fused = P.passes;
     }
-    if (!stealing) {                                   // the launch's only queue: its own shard
+    if (!have_blocks) {                                // the launch's only queue: its own shard
         P.n_queues  = 1;
-        P.queues[0] = RtQueue{P.work_counter, P.accum, opt.shard_index, L.n_tiles};
+        RtQueue q{};
+        q.work_counter = P.work_counter; q.accum = P.accum; q.tile_first = opt.shard_index; q.n_tiles = L.n_tiles;
+        P.queues[0] = q;
     }
     if ((uint64_t)slots * P.passes >= 0x7fffff00ull) throw std::runtime_error("frame shard exceeds 2^31 work slots; use more shards or fewer passes");
 
@@ -413,12 +446,38 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     uint64_t       reserve = work_slots / (warps * 64u) / 32u * 32u;
     P.reserve = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(reserve, 32u), 256u);
 
+    // per-tile completion flags for a host that hands tiles on while the kernel still runs (pixel items, whole frame)
+    if (want_tile_flags && !L.sample_items && trace && !L.compact && opt.shard_count <= 1 && !opt.no_resolve) {
+        const size_t tiles = (H + opt.tile_rows - 1) / opt.tile_rows;
+        if (ctx.tile_cap < tiles) {
+            RT_CUDA(cudaStreamSynchronize(stream));
+            if (ctx.d_tile_done) RT_CUDA(cudaFree(ctx.d_tile_done));
+            if (ctx.h_tile_flags) RT_CUDA(cudaFreeHost(ctx.h_tile_flags));
+            ctx.d_tile_done = nullptr; ctx.h_tile_flags = nullptr; ctx.tile_cap = 0;
+            RT_CUDA(cudaMalloc(&ctx.d_tile_done, tiles * sizeof(unsigned int)));
+            RT_CUDA(cudaMallocHost(&ctx.h_tile_flags, tiles * sizeof(unsigned int)));
+            std::memset(ctx.h_tile_flags, 0, tiles * sizeof(unsigned int));
+            ctx.tile_cap = tiles;
+            ctx.tile_epoch = 0;
+        }
+        if (++ctx.tile_epoch == 0u) { std::memset(ctx.h_tile_flags, 0, ctx.tile_cap * sizeof(unsigned int)); ctx.tile_epoch = 1u; }
+        void* flags_dev = nullptr;
+        RT_CUDA(cudaHostGetDevicePointer(&flags_dev, ctx.h_tile_flags, 0));
+        RT_CUDA(cudaMemsetAsync(ctx.d_tile_done, 0, tiles * sizeof(unsigned int), stream));
+        P.tile_done  = ctx.d_tile_done;
+        P.tile_flags = static_cast<unsigned int*>(flags_dev);
+        P.tile_epoch = ctx.tile_epoch;
+        L.tile_flags = true;
+    }
+
     if (L.n_tiles > 0 || stealing) {
         RT_CUDA(cudaMemsetAsync(L.slot, 0, sizeof(CounterSlot), stream));
         // fused passes: no stale sums may look like a finished pass.  Stream order puts this BEFORE the reset
         // of the work counter, so no other GPU can be handed a slot of this shard while its sums are cleared.
         if (fused) RT_CUDA(cudaMemsetAsync(P.accum, 0, L.out_pixels * sizeof(RtFloat4), stream));
-        if (stealing) RT_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), stream));
+        // tile counters of this shard's block, then (last) its work counter: nobody can be handed one of its slots earlier
+        if (gathering) RT_CUDA(cudaMemsetAsync(own_block + BL.off_tiles, 0, BL.off_accum - BL.off_tiles, stream));
+        if (have_blocks) RT_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), stream));
         if (timed) RT_CUDA(cudaEventRecord(ctx.ev0, stream));
         if (!L.sample_items) {
             RT_CUDA(opt.fast_math ? launch_render_fast(P, scene.view, L.grid, L.smem_limit, stream)
@@ -538,11 +597,36 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
     if (zero_copy) zc_opt.full_frame_out = true;            // tiles land at their frame offsets
     const ShardLaunch L = enqueue_shard(ctx, scene, camera, W, H, zero_copy ? zc_opt : opt,
                                         zero_copy ? static_cast<uint32_t*>(zero_copy) : static_cast<uint32_t*>(device_pixels),
-                                        device_accum, stream, opt.stats != nullptr);
+                                        device_accum, stream, opt.stats != nullptr, staged_zero_copy);
     const uint32_t n_tiles = L.n_tiles;
     uint32_t*      d_out   = L.d_out;
 
-    if (zero_copy) {
+    if (zero_copy && L.tile_flags) {
+        // The kernel flags every finished 16-row tile (bottom rows first); its rows go from the staging frame to the
+        // caller's frame while the rest is still being rendered, so that only the last tile's copy follows the kernel.
+        const size_t tiles = (H + opt.tile_rows - 1) / opt.tile_rows, tile_bytes = (size_t)opt.tile_rows * W * 4;
+        const volatile unsigned int* flags = ctx.h_tile_flags;
+        std::vector<unsigned char> copied(tiles, 0);
+        size_t left = tiles;
+        bool   finished = false;
+        while (left) {
+            size_t progressed = 0;
+            for (size_t t = tiles; t-- > 0;) {
+                if (copied[t] || flags[t] != ctx.tile_epoch) continue;
+                std::atomic_thread_fence(std::memory_order_acquire);
+                const size_t off = t * tile_bytes, cnt = std::min(tile_bytes, (size_t)W * H * 4 - off);
+                std::memcpy(reinterpret_cast<unsigned char*>(host_pixels) + off, ctx.h_stage + off, cnt);
+                copied[t] = 1; --left; ++progressed;
+            }
+            if (left && !progressed) {
+                if (finished) throw std::runtime_error("render kernel finished without completing every tile");
+                const cudaError_t q = cudaStreamQuery(stream);
+                if (q == cudaSuccess) finished = true;             // one more sweep picks up the last flags
+                else if (q != cudaErrorNotReady) fail("render kernel", q);
+            }
+        }
+        RT_CUDA(cudaStreamSynchronize(stream));
+    } else if (zero_copy) {
         RT_CUDA(cudaStreamSynchronize(stream));
         if (staged_zero_copy) {              // this shard's rows of the staging frame -> the caller's frame
             const size_t tile_px = (size_t)opt.tile_rows * W;
@@ -693,7 +777,8 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
         }
     }
     static const bool steal_enabled = [] { const char* e = std::getenv("RT_STEAL"); return !(e && *e == '0'); }();
-    const bool steal = peer && all_peer && steal_enabled;
+    static const bool gather_enabled = [] { const char* e = std::getenv("RT_TILE_GATHER"); return !(e && *e == '0'); }();
+    const bool steal = peer && all_peer;               // shard blocks: work stealing and/or tile gather
     DeviceContext& c0 = *ctxs[0];
     RT_CUDA(cudaSetDevice(0));
     if (c0.d_out_cap < (size_t)W * H) {
@@ -706,7 +791,7 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
     // shard blocks: every device's work counter (+ the sums of fused passes), reachable from all the others
     std::vector<PeerQueue> blocks;
     if (steal) {
-        const size_t need = base.passes > 1 ? shard_block_bytes(W, H) : kBlockHeader;
+        const size_t need = shard_block_bytes(W, H);
         for (int d = 0; d < N; ++d) {
             DeviceContext& c = *ctxs[d];
             if (c.d_block_cap < need) {
@@ -736,6 +821,9 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
                 blocks[i] = PeerQueue{ctxs[e]->d_block, (uint32_t)e, 0u};
             }
             o.peer_queues = blocks.data(); o.n_peer_queues = (uint32_t)N;
+            o.no_steal    = !steal_enabled;
+            o.tile_gather = gather_enabled;
+            o.gather_shard = 0;
         }
         launches[d] = enqueue_shard(*ctxs[d], device_scene(world, *ctxs[d]), camera, W, H, o,
                                     peer ? c0.d_out : nullptr, nullptr, ctxs[d]->stream, true);
@@ -894,7 +982,7 @@ void device_free(void* p)
     cudaFree(p);
 }
 
-size_t shard_block_bytes(size_t width, size_t height) { return kBlockHeader + width * height * sizeof(RtFloat4); }
+size_t shard_block_bytes(size_t width, size_t height) { return block_layout(width, height).bytes; }
 void   shard_block_init(void* block)
 {
     if (!block) throw std::runtime_error("shard_block_init: null block");

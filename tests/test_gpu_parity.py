@@ -331,6 +331,29 @@ def test_pinned_and_pageable_destinations_agree(gpu_rt, scenes):
     assert np.array_equal(a, b)
 
 
+def test_pageable_frames_never_mix_consecutive_frames(gpu_rt, scenes):
+    """A pageable destination is filled tile by tile WHILE the kernel renders (per-tile completion flags, staging
+    frame reused from call to call).  If a tile were handed over before all of its pixels had landed, the caller
+    would see pixels of the PREVIOUS frame: alternate two very different views for 40 frames and compare every one
+    with the frame a pinned destination receives (no staging, no flags)."""
+    rt = gpu_rt
+    W, H, spp, depth = 1920, 1080, 32, 8
+    views = []
+    for text, move in ((scenes.default_world(), (0.0, 0.0, 0.0)), (scenes.example_world(), (1.5, 0.75, 0.5))):
+        h = rt.load_world(text)
+        rt.move_camera_position(h, *move)
+        fb = rt.Framebuffer(W, H, pinned=True)
+        rt.render_with_options(fb, h, rt.Options(spp, depth))
+        views.append((h, fb.pixels.copy()))
+    assert not np.array_equal(views[0][1], views[1][1])
+    fb = rt.Framebuffer(W, H, pinned=False)
+    for i in range(40):
+        h, want = views[i & 1]
+        fb.pixels[...] = 0x5A
+        rt.render_with_options(fb, h, rt.Options(spp, depth))
+        assert np.array_equal(fb.pixels, want), f"frame {i}: {(fb.pixels != want).any(axis=2).sum()} pixels differ"
+
+
 def test_interactive_progressive_frame(gpu_rt, ob, scenes):
     """rt_render_progressive: 5 calls of 3 spp == one 15-spp frame bit for bit; a
     camera move (GameView.swift:198-216) or a resize restarts the accumulation."""
@@ -618,12 +641,15 @@ def _blocks(rt, W, H, n):
     return b
 
 
-@pytest.mark.parametrize("passes", [1, 4])
-def test_work_stealing_queues_on_one_gpu(gpu_rt, ob, scenes, passes):
+@pytest.mark.parametrize("passes,tile_gather", [(1, True), (4, True), (1, False), (4, False)])
+def test_work_stealing_queues_on_one_gpu(gpu_rt, ob, scenes, passes, tile_gather):
     """Cross-GPU work stealing, exercised deterministically on ONE device: three shard blocks whose owners
     never start (their counters stay 0 = 'everything unassigned'); the launch of shard 0 renders its own
     tiles, then raids queues 2 and 1 until the whole frame is done — every stolen pixel-pass reads and
-    writes the sums in its victim's block.  Frame and ray count equal the oracle's."""
+    writes the sums in its victim's block.  Frame and ray count equal the oracle's.
+    tile_gather: the pixels of shards 1 and 2 are collected in THEIR blocks' frames and every completed 8-row tile is
+    copied into the destination as 16-byte vectors (shard 0 is the gathering shard and writes in place); the ragged
+    frame (200 x 117: a last tile of 5 rows, 1000 pixels) also exercises the unaligned tail of the copy."""
     import torch
     rt = gpu_rt
     W, H, spp, depth = 200, 117, 8, 8
@@ -636,6 +662,7 @@ def test_work_stealing_queues_on_one_gpu(gpu_rt, ob, scenes, passes):
     torch.cuda.synchronize()
     st = rt.RenderStats()
     o = rt.Options(spp, depth, passes=passes, tile_rows=8, shard_index=0, shard_count=3, full_frame_out=True,
+                   tile_gather=tile_gather,
                    peer_queues=[(blocks[0].data_ptr(), 0), (blocks[2].data_ptr(), 2), (blocks[1].data_ptr(), 1)])
     rt.render_device(h, o, W, H, out.data_ptr(), 0, 0, st)
     torch.cuda.synchronize()
@@ -648,6 +675,7 @@ def test_work_stealing_queues_on_one_gpu(gpu_rt, ob, scenes, passes):
     out2 = torch.zeros((H, W), dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
     o2 = rt.Options(spp, depth, passes=passes, tile_rows=8, shard_index=1, shard_count=3, full_frame_out=True,
+                    tile_gather=tile_gather,
                     peer_queues=[(blocks[1].data_ptr(), 1), (blocks[2].data_ptr(), 2), (blocks[0].data_ptr(), 0)])
     s2 = rt.RenderStats()
     rt.render_device(h, o2, W, H, out2.data_ptr(), 0, 0, s2)
