@@ -557,7 +557,7 @@ def main():
                    "parallelism": (f"row-tile shards x{n_gpus} (static boustrophedon deal"
                                    + (" + cross-GPU work stealing of the tail over NVLink atomics" if steal_on else "")
                                    + f"), {gather} gather to rank 0 "
-                                   + ("(tiles stored by the render kernels into rank 0's frame over NVLink, CUDA IPC)"
+                                   + ("(fused into the render kernels: every finished pixel is stored into rank 0's frame over NVLink, CUDA IPC)"
                                       if gather == "peer" else "(compact buffers + dist.gather)"))
                    if n_gpus > 1 else "1 GPU",
                    "stolen_slots_first_step": int(stolen_first) if n_gpus > 1 else 0,

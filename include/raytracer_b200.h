@@ -30,9 +30,6 @@ extern "C" {
                                       Worlds with fewer than 64 spheres ignore it. */
 #define RT_OPT_RESOLVE_EACH_PASS 0x200u /* passes > 1: refresh the RGBA8 frame after every pass, not only the last */
 #define RT_OPT_NO_STEAL      0x400u /* peer_queues given: no cross-GPU work stealing (static tile deal only) */
-#define RT_OPT_NO_TILE_GATHER 0x800u /* peer_queues given: every finished pixel is stored straight into device_pixels
-                                        (one 4-byte store across NVLink per pixel) instead of being collected in the
-                                        owner's block and copied tile by tile as 16-byte vectors */
 #define RT_OPT_FULL_FRAME_OUT 0x20u /* rt_render_device with shard_count > 1: device_pixels / device_accum are
                                        FULL width*height frames (e.g. another GPU's frame mapped through CUDA IPC
                                        or peer access); this shard's tiles are stored at their frame offsets */
@@ -97,11 +94,7 @@ typedef struct RtRenderOptions {
                                   single-pass frame bit for bit (common.rs:338-340 adds the samples in order). */
   uint32_t n_peer_queues;      /* rt_render_device, shard_count > 1, RT_OPT_FULL_FRAME_OUT: cross-GPU work stealing. */
   const RtPeerQueue *peer_queues; /* The blocks of ALL shard_count shards (this shard's own included), in the order
-                                  in which the others are raided once this shard's own queue is empty.  With blocks
-                                  the frame is also GATHERED through them: finished pixels are collected in the
-                                  owner's block and each completed 16-row tile is copied into device_pixels — which
-                                  must be the frame in the memory of the GPU that renders shard 0 — as 16-byte
-                                  vectors (RT_OPT_NO_TILE_GATHER: plain per-pixel stores instead). */
+                                  in which the others are raided once this shard's own queue is empty. */
 } RtRenderOptions;
 
 /* Thread-local text of the last failure of any call in this library ("" if none). */

@@ -58,16 +58,13 @@ struct CounterSlot {            // 16 B, zeroed by one memset per launch
 // the float4 sums of the fused passes for the full frame.  Lives in its owner's device memory; the
 // other GPUs reach it through peer access or a CUDA-IPC mapping.
 constexpr size_t       kBlockHeader    = 256;
-// layout of a shard block for a width x height frame: [header][tile counters, one per 4-row tile at most][float4 sums]
-// [RGBA8 frame]; the last three are indexed like the full frame
-struct BlockLayout { size_t off_tiles, off_accum, off_frame, bytes; };
+// layout of a shard block for a width x height frame: [header: the work counter][float4 sums, indexed like the frame]
+struct BlockLayout { size_t off_accum, bytes; };
 BlockLayout block_layout(size_t W, size_t H)
 {
     BlockLayout b;
-    b.off_tiles = kBlockHeader;
-    b.off_accum = b.off_tiles + ((((H + 3) / 4) * sizeof(unsigned int) + 255) & ~(size_t)255);
-    b.off_frame = b.off_accum + W * H * sizeof(RtFloat4);
-    b.bytes     = b.off_frame + W * H * sizeof(uint32_t);
+    b.off_accum = kBlockHeader;
+    b.bytes     = b.off_accum + W * H * sizeof(RtFloat4);
     return b;
 }
 constexpr unsigned int kQueueExhausted = 0xC0000000u;   // any value >= every queue length (< 2^31)
@@ -351,7 +348,6 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     const BlockLayout BL = block_layout(W, H);
     const bool     have_blocks = opt.n_peer_queues > 0 && !L.sample_items && trace;
     const bool     stealing    = have_blocks && opt.n_peer_queues > 1 && !opt.no_steal;
-    const bool     gathering   = have_blocks && opt.tile_gather && !opt.no_resolve && L.d_out != nullptr;
     unsigned char* own_block = nullptr;
     for (uint32_t i = 0; i < opt.n_peer_queues; ++i)
         if (opt.peer_queues[i].shard_index == opt.shard_index) own_block = static_cast<unsigned char*>(opt.peer_queues[i].block);
@@ -360,9 +356,6 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
         RtQueue q{};
         q.work_counter = reinterpret_cast<unsigned int*>(b);
         q.accum        = reinterpret_cast<RtFloat4*>(b + BL.off_accum);
-        q.tile_done    = reinterpret_cast<unsigned int*>(b + BL.off_tiles);
-        // the shard on the gathering GPU writes its pixels straight into the destination frame
-        q.frame        = (gathering && shard == opt.gather_shard) ? L.d_out : reinterpret_cast<uint32_t*>(b + BL.off_frame);
         q.tile_first   = shard;
         q.n_tiles      = shard_tile_count(H, opt.tile_rows, shard, opt.shard_count);
         return q;
@@ -380,7 +373,6 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
                 P.queues[n++] = queue_of(static_cast<unsigned char*>(pq.block), pq.shard_index);
             }
         P.n_queues = n;
-        if (gathering) P.gather_dst = L.d_out;
     }
 
     // Progressive passes fused into this launch (rt_types.h): needs a fresh frame (the alpha sum tags the
@@ -475,8 +467,6 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
         // fused passes: no stale sums may look like a finished pass.  Stream order puts this BEFORE the reset
         // of the work counter, so no other GPU can be handed a slot of this shard while its sums are cleared.
         if (fused) RT_CUDA(cudaMemsetAsync(P.accum, 0, L.out_pixels * sizeof(RtFloat4), stream));
-        // tile counters of this shard's block, then (last) its work counter: nobody can be handed one of its slots earlier
-        if (gathering) RT_CUDA(cudaMemsetAsync(own_block + BL.off_tiles, 0, BL.off_accum - BL.off_tiles, stream));
         if (have_blocks) RT_CUDA(cudaMemsetAsync(P.work_counter, 0, sizeof(unsigned int), stream));
         if (timed) RT_CUDA(cudaEventRecord(ctx.ev0, stream));
         if (!L.sample_items) {
@@ -777,8 +767,7 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
         }
     }
     static const bool steal_enabled = [] { const char* e = std::getenv("RT_STEAL"); return !(e && *e == '0'); }();
-    static const bool gather_enabled = [] { const char* e = std::getenv("RT_TILE_GATHER"); return !(e && *e == '0'); }();
-    const bool steal = peer && all_peer;               // shard blocks: work stealing and/or tile gather
+    const bool steal = peer && all_peer;               // shard blocks (work counters + sums) reachable from every device
     DeviceContext& c0 = *ctxs[0];
     RT_CUDA(cudaSetDevice(0));
     if (c0.d_out_cap < (size_t)W * H) {
@@ -791,7 +780,7 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
     // shard blocks: every device's work counter (+ the sums of fused passes), reachable from all the others
     std::vector<PeerQueue> blocks;
     if (steal) {
-        const size_t need = shard_block_bytes(W, H);
+        const size_t need = base.passes > 1 ? shard_block_bytes(W, H) : kBlockHeader;
         for (int d = 0; d < N; ++d) {
             DeviceContext& c = *ctxs[d];
             if (c.d_block_cap < need) {
@@ -822,8 +811,6 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
             }
             o.peer_queues = blocks.data(); o.n_peer_queues = (uint32_t)N;
             o.no_steal    = !steal_enabled;
-            o.tile_gather = gather_enabled;
-            o.gather_shard = 0;
         }
         launches[d] = enqueue_shard(*ctxs[d], device_scene(world, *ctxs[d]), camera, W, H, o,
                                     peer ? c0.d_out : nullptr, nullptr, ctxs[d]->stream, true);

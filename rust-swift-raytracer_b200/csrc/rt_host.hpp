@@ -139,11 +139,6 @@ struct Options {
     const PeerQueue* peer_queues   = nullptr;
     uint32_t         n_peer_queues = 0;
     bool     no_steal       = false;        // peer_queues given, but every GPU traces only its own shard
-    // Tile gather (with peer_queues): finished pixels are collected in the owner's block and every completed tile is
-    // copied to device_pixels — the destination frame, in the memory of the GPU that renders shard `gather_shard` —
-    // as one contiguous run of 16-byte vectors, instead of one 4-byte store per pixel across NVLink.
-    bool     tile_gather    = true;
-    uint32_t gather_shard   = 0;
     RenderStats* stats      = nullptr;
 };
 

@@ -150,35 +150,6 @@ __device__ __forceinline__ void accum_store(RtFloat4* p, float4 v)
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Tile gather: the warp copies one finished tile — rows*width RGBA8 pixels, one contiguous byte range of the
-// row-major frame — from the owner's frame to the destination frame as 16-byte vectors (512 contiguous bytes per
-// warp and step: full NVLink packets instead of one 4-byte store per pixel).  Loads bypass L1 (other SMs and, for
-// stolen pixels, other GPUs wrote the source); the stores need no ordering of their own, the host reads the
-// destination only after every kernel of the frame has finished.
-// (__noinline__: a rare event — the render loop's register allocation must not pay for it)
-static __device__ __noinline__ void gather_copy_tile(const RtFrameParams& P, uint32_t tile, uint32_t lq, uint32_t lane,
-                                              uint32_t step = 32u)
-{
-    const uint32_t first = tile * P.tile_rows * P.width;
-    const uint32_t rows  = min((tile + 1u) * P.tile_rows, P.height) - tile * P.tile_rows;
-    const uint32_t n     = rows * P.width;
-    const uint32_t* src  = P.queues[lq].frame + first;
-    uint32_t*       dst  = P.gather_dst + first;
-    __threadfence_system();                                    // acquire: the counts this warp observed order the pixels
-    const uint32_t n4 = n >> 2;                                // first is a multiple of 4 pixels (tile_rows is)
-    for (uint32_t i = lane; i < n4; i += step) {
-        uint4 v;
-        asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(reinterpret_cast<const uint4*>(src) + i) : "memory");
-        reinterpret_cast<uint4*>(dst)[i] = v;
-    }
-    for (uint32_t i = (n4 << 2) + lane; i < n; i += step) {
-        uint32_t v;
-        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src + i) : "memory");
-        dst[i] = v;
-    }
-}
-
 #ifndef RT_MIN_CTAS_SMALL
 #define RT_MIN_CTAS_SMALL 4   // 256-thread CTAs per SM the register allocation must allow (<= 64 registers)
 #endif
@@ -257,30 +228,7 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
         L[p].o = L[p].pend = L[p].thr = mk(0.f, 0.f, 0.f);
     }
     uint32_t segments = 0;
-    // tile gather: tiles (tile | queue << 24) a lane of this warp has just completed, kept in shared memory — not in
-    // a register of the 64-register kernels — until the whole warp copies them at the top of the next iteration
-    constexpr uint32_t kGatherSlots = 4u;
-    __shared__ unsigned int rt_gather[BLOCK / 32][kGatherSlots + 1u];
-    unsigned int* const gq = rt_gather[threadIdx.x >> 5];
-    if (lane == 0) gq[0] = 0u;
-    __syncwarp();
-
     for (;;) {
-        // ---- 0. tile gather: tiles completed in the last iteration are copied by the whole warp ----
-        if (P.gather_dst) {
-            __syncwarp();
-            const uint32_t n = min(gq[0], kGatherSlots);
-            if (n) {
-                for (uint32_t i = 0; i < n; ++i) {
-                    const uint32_t t = gq[1u + i];
-                    gather_copy_tile(P, t & 0xffffffu, t >> 24, lane);
-                }
-                __syncwarp();
-                if (lane == 0) gq[0] = 0u;
-                __syncwarp();
-            }
-        }
-
         // ---- 1. paths without a pixel take the next slots of the warp's slab ----
         bool any_have = false;
 #pragma unroll
@@ -405,23 +353,10 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
                 if (!last || (P.flags & RT_FLAG_ACCUM_OUT))
                     accum_store(&ac[Lp.out_index], make_float4(Lp.acc_r, Lp.acc_g, Lp.acc_b, acc_a));
                 if (last ? !(P.flags & RT_FLAG_NO_RESOLVE) : (P.flags & RT_FLAG_RESOLVE_EACH_PASS) != 0u) {
-                    uint32_t* frame = P.gather_dst ? P.queues[(Lp.ctl >> 16) & 0xffu].frame : P.out;
-                    frame[Lp.out_index] = resolve_pixel<FAST>(Lp.acc_r, Lp.acc_g, Lp.acc_b, acc_a,
+                    P.out[Lp.out_index] = resolve_pixel<FAST>(Lp.acc_r, Lp.acc_g, Lp.acc_b, acc_a,
                                                               last ? P.resolve_spp : P.sample_begin + pass_end);
                 }
-                if (last && P.gather_dst) {            // tile gather: count the pixel in its owner's tile counter
-                    const uint32_t lq = (Lp.ctl >> 16) & 0xffu;
-                    if (P.queues[lq].frame != P.gather_dst) {          // (the gathering GPU's own tiles are already in place)
-                        const uint32_t tile = (Lp.out_index / P.width) / P.tile_rows;
-                        const uint32_t rows = min((tile + 1u) * P.tile_rows, P.height) - tile * P.tile_rows;
-                        __threadfence_system();        // the pixel is out (in its owner's memory) before it is counted
-                        if (atomicAdd_system(&P.queues[lq].tile_done[tile], 1u) + 1u == rows * P.width) {
-                            const uint32_t k = atomicAdd(&gq[0], 1u);
-                            if (k < kGatherSlots) gq[1u + k] = tile | (lq << 24);
-                            else gather_copy_tile(P, tile, lq, 0u, 1u);      // (never seen) more than 4 at once: copy alone
-                        }
-                    }
-                } else if (last && P.tile_done) {      // full-frame output: out_index = image_row * width + column
+                if (last && P.tile_done) {      // full-frame output: out_index = image_row * width + column
                     const uint32_t tile  = (Lp.out_index / P.width) / P.tile_rows;
                     const uint32_t rows  = min((tile + 1u) * P.tile_rows, P.height) - tile * P.tile_rows;
                     __threadfence();                   // this pixel is ordered before its count (device scope: cheap) ...

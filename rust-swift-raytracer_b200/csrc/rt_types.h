@@ -141,13 +141,6 @@ enum : uint32_t {
 struct RtQueue {
     unsigned int* work_counter;   // next unassigned slot of this shard (reset by its owner before every frame)
     RtFloat4*     accum;          // this shard's float4 sums (fused passes), indexed like `out`
-    // Tile gather (RtFrameParams::gather_dst): the shard's finished RGBA8 pixels land in `frame` — a full-frame-
-    // indexed buffer in the OWNER's memory (plain local stores for the owner, the few stolen pixels come over
-    // NVLink) — and tile_done[t] counts them; whoever completes a tile copies its rows, as one contiguous range of
-    // 16-byte vectors, into the destination frame on the gathering GPU.  For the shard that lives on the gathering
-    // GPU `frame` IS the destination and nothing is copied.
-    unsigned int* tile_done;
-    uint32_t*     frame;
     uint32_t      tile_first;     // shard index: the queue's tiles are rt_shard_tile(tile_first, tile_stride, j)
     uint32_t      n_tiles;
 };
@@ -190,8 +183,8 @@ struct RtFrameParams {
     // that the host can hand the tile's rows on while the kernel is still rendering the rest of the frame.
     unsigned int* tile_done;
     unsigned int* tile_flags;
-    uint32_t* gather_dst;    // tile gather: the destination frame (usually another GPU's memory); null: pixels go to `out`
     uint32_t  tile_epoch;
+    uint32_t  pad_tile;
     uint32_t  n_queues;      // >= 1
     RtQueue   queues[RT_MAX_QUEUES];   // [0] = the launch's own shard (work_counter / accum above), then the peers
 };

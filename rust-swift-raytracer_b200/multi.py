@@ -103,8 +103,7 @@ class ShardedRenderer:
     """
 
     def __init__(self, rt, handle, width: int, height: int, rank: int = 0, world: int = 1,
-                 tile_rows: int = 16, device=None, gather: Optional[str] = None, steal: bool = True,
-                 tile_gather: bool = True):
+                 tile_rows: int = 16, device=None, gather: Optional[str] = None, steal: bool = True):
         self.rt, self.handle = rt, handle
         self.width, self.height, self.rank, self.world, self.tile_rows = width, height, rank, world, tile_rows
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -118,8 +117,6 @@ class ShardedRenderer:
         self._peer_blocks = {}    # rank -> mapped address of its shard block
         self.queues = None        # [(block address, shard index)] own first, then (rank+1), (rank+2), ...
         self.steal = False        # cross-GPU work stealing is on
-        self.tile_gather = False  # finished tiles travel as 16-byte vector copies (else: one 4-byte store per pixel)
-        self._want_steal, self._want_gather = steal, tile_gather
         if self.gather == "peer" and world > 1:
             # Map rank 0's frame into every rank.  CUDA IPC can be unavailable (containers without a
             # shared IPC namespace, no peer access): all ranks then agree to use the NCCL gather — a
@@ -154,7 +151,7 @@ class ShardedRenderer:
                 self.token.zero_()
                 self.local = None
                 self.staging = None
-                if (steal or tile_gather) and world <= 8 and not os.environ.get("RT_DISABLE_BLOCKS"):
+                if steal and world <= 8 and not os.environ.get("RT_DISABLE_STEAL"):
                     self._exchange_blocks()
         if not (self.gather == "peer" and world > 1):
             self.gather = "nccl"
@@ -192,13 +189,13 @@ class ShardedRenderer:
             return
         order = [(self.rank + i) % self.world for i in range(self.world)]
         self.queues = [((self.block_ptr if r == self.rank else self._peer_blocks[r]), r) for r in order]
-        self.steal, self.tile_gather = bool(self._want_steal), bool(self._want_gather)
+        self.steal = True
 
     def _release_blocks(self):
         for p in self._peer_blocks.values():
             self.rt.ipc_close(p)
         self._peer_blocks = {}
-        self.queues, self.steal, self.tile_gather = None, False, False
+        self.queues, self.steal = None, False
 
     def close(self):
         if self.frame_ptr or self.block_ptr:
@@ -233,8 +230,7 @@ class ShardedRenderer:
         out_ptr = self.frame_ptr if peer else self.local.data_ptr()
         o = rt.Options(spp, depth, passes=passes, resolve_spp=spp, fast_math=fast_math, fixed_jitter=fixed_jitter,
                        tile_rows=self.tile_rows, shard_index=self.rank, shard_count=self.world,
-                       full_frame_out=peer, group_cull=group_cull, peer_queues=self.queues,
-                       no_steal=not self.steal, tile_gather=self.tile_gather)
+                       full_frame_out=peer, group_cull=group_cull, peer_queues=self.queues if self.steal else None)
         if seed is not None:
             o.seed = seed
         st = stats if stats is not None else (rt.RenderStats() if count_rays else None)

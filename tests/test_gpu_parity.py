@@ -641,15 +641,12 @@ def _blocks(rt, W, H, n):
     return b
 
 
-@pytest.mark.parametrize("passes,tile_gather", [(1, True), (4, True), (1, False), (4, False)])
-def test_work_stealing_queues_on_one_gpu(gpu_rt, ob, scenes, passes, tile_gather):
+@pytest.mark.parametrize("passes", [1, 4])
+def test_work_stealing_queues_on_one_gpu(gpu_rt, ob, scenes, passes):
     """Cross-GPU work stealing, exercised deterministically on ONE device: three shard blocks whose owners
     never start (their counters stay 0 = 'everything unassigned'); the launch of shard 0 renders its own
     tiles, then raids queues 2 and 1 until the whole frame is done — every stolen pixel-pass reads and
-    writes the sums in its victim's block.  Frame and ray count equal the oracle's.
-    tile_gather: the pixels of shards 1 and 2 are collected in THEIR blocks' frames and every completed 8-row tile is
-    copied into the destination as 16-byte vectors (shard 0 is the gathering shard and writes in place); the ragged
-    frame (200 x 117: a last tile of 5 rows, 1000 pixels) also exercises the unaligned tail of the copy."""
+    writes the sums in its victim's block.  Frame and ray count equal the oracle's."""
     import torch
     rt = gpu_rt
     W, H, spp, depth = 200, 117, 8, 8
@@ -662,7 +659,6 @@ def test_work_stealing_queues_on_one_gpu(gpu_rt, ob, scenes, passes, tile_gather
     torch.cuda.synchronize()
     st = rt.RenderStats()
     o = rt.Options(spp, depth, passes=passes, tile_rows=8, shard_index=0, shard_count=3, full_frame_out=True,
-                   tile_gather=tile_gather,
                    peer_queues=[(blocks[0].data_ptr(), 0), (blocks[2].data_ptr(), 2), (blocks[1].data_ptr(), 1)])
     rt.render_device(h, o, W, H, out.data_ptr(), 0, 0, st)
     torch.cuda.synchronize()
@@ -675,8 +671,7 @@ def test_work_stealing_queues_on_one_gpu(gpu_rt, ob, scenes, passes, tile_gather
     out2 = torch.zeros((H, W), dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
     o2 = rt.Options(spp, depth, passes=passes, tile_rows=8, shard_index=1, shard_count=3, full_frame_out=True,
-                    tile_gather=tile_gather,
-                    peer_queues=[(blocks[1].data_ptr(), 1), (blocks[2].data_ptr(), 2), (blocks[0].data_ptr(), 0)])
+                     peer_queues=[(blocks[1].data_ptr(), 1), (blocks[2].data_ptr(), 2), (blocks[0].data_ptr(), 0)])
     s2 = rt.RenderStats()
     rt.render_device(h, o2, W, H, out2.data_ptr(), 0, 0, s2)
     torch.cuda.synchronize()
