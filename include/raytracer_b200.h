@@ -128,7 +128,10 @@ void rt_progressive_reset(const struct Rust_WorldHandle *handle);
  * device memory — the full width*height frame when shard_count <= 1, otherwise this shard's
  * tiles packed back to back (rt_shard_pixel_count pixels).  device_accum: optional float4
  * sums, same indexing.  stream: a cudaStream_t, or NULL for the library's own stream
- * (then the call returns after the kernel has finished).  Returns 0 on success. */
+ * (then the call returns after the kernel has finished).  With a stream the call returns as soon as the work is
+ * enqueued — unless the render needs the library's per-device scratch (sample-item scheduling of heavy scenes, fused
+ * passes without a caller accumulator), which every launch on the device shares: then it returns after the kernel has
+ * finished, so that renders in flight on different streams of one device never share scratch.  Returns 0 on success. */
 int rt_render_device(const struct Rust_WorldHandle *handle, const RtRenderOptions *options,
                      size_t width, size_t height, void *device_pixels, void *device_accum,
                      void *stream);

@@ -222,6 +222,7 @@ struct ShardLaunch {
     bool         resident = false, filtered = false, culled = false, sample_items = false;
     uint32_t     launches = 0, passes_fused = 0, paths_per_lane = 1;
     bool         tile_flags = false;       // the kernel publishes per-tile completion flags (ctx.h_tile_flags, ctx.tile_epoch)
+    bool         uses_scratch = false;     // the launch reads/writes per-device scratch (sample buffer, hand-over sums, frame)
     CounterSlot* slot = nullptr;
     uint32_t*    d_out = nullptr;
 };
@@ -462,6 +463,7 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
         L.tile_flags = true;
     }
 
+    L.uses_scratch = L.sample_items || (P.accum && P.accum == ctx.d_accum) || (L.d_out && L.d_out == ctx.d_out);
     if (L.n_tiles > 0 || stealing) {
         RT_CUDA(cudaMemsetAsync(L.slot, 0, sizeof(CounterSlot), stream));
         // fused passes: no stale sums may look like a finished pass.  Stream order puts this BEFORE the reset
@@ -678,7 +680,10 @@ void ray_trace_into(const World& world, const Camera& camera, size_t width, size
                 copy_frame(host32 + frame_px, ctx.h_stage + dev_px * 4, count * 4);
             });
         }
-    } else if (!user_stream) {
+    } else if (!user_stream || L.uses_scratch) {
+        // A caller's stream normally gets the work enqueued and the call returns; but the per-device scratch (sample
+        // buffer of the sample-item mode, hand-over sums, internal frame) is shared by every launch on the device, so
+        // a launch that uses it is finished before the next one — possibly on another stream — may be enqueued.
         RT_CUDA(cudaStreamSynchronize(stream));
     }
 

@@ -856,3 +856,30 @@ def test_multi_gpu_tile_gather_when_two_devices(gpu_rt, scenes):
     for i in range(2):
         rt.render_with_options(fb, h, rt.Options(2, 8, shard_index=i, shard_count=2, device=i))
     assert np.array_equal(fb.pixels, full)
+
+
+def test_two_paths_per_lane_kernels_are_bit_identical(scenes, tmp_path):
+    """RT_PATHS_PER_LANE=2 (read once per process) selects the FILTER kernels that carry two paths per lane and test
+    both rays against every primitive pair they load: same frames, same ray counts, pixel and sample items alike."""
+    import subprocess
+    import sys
+    code = r'''
+import importlib, sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle_binding as ob
+rt = importlib.import_module("rust-swift-raytracer_b200"); scenes = importlib.import_module("rust-swift-raytracer_b200.scenes")
+for text, W, H, spp, depth in ((scenes.c3_world(), 160, 90, 3, 8), (scenes.synthetic_world(800, 200, seed=10000), 96, 54, 2, 16)):
+    cam, world = ob.parse_input(text)
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    h = rt.load_world(text)
+    for items in (False, True):
+        fb = rt.Framebuffer(W, H); st = rt.RenderStats()
+        rt.render_with_options(fb, h, rt.Options(spp, depth, sample_items=items), st)
+        assert st.paths_per_lane == 2 and st.filtered == 1, (st.paths_per_lane, st.filtered)
+        assert st.rays == rays and np.array_equal(fb.pixels, want), items
+print("ok")
+''' % (str(ROOT), str(ROOT / "oracle"))
+    import os
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, RT_PATHS_PER_LANE="2"))
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
