@@ -215,6 +215,10 @@ double rt_measure_fp32_peak(int device);
  * against the compiler's IEEE divide on `operand_sets` pseudo-random operand sets.  Returns
  * the number of sets whose quotients differ in any bit (0 expected), negative on failure. */
 long long rt_selftest_division(int device, unsigned long long operand_sets, uint32_t seed);
+/* GPU self-test: the exact kernel's range-guarded square root (the compiler's own correctly rounded sequence without
+ * its per-call range branch) against sqrtf on EVERY float bit pattern.  Returns the number of patterns whose bits
+ * differ or whose range predicate is wrong (0 expected), negative on failure. */
+long long rt_selftest_sqrt(int device);
 
 #ifdef __cplusplus
 }

@@ -104,7 +104,7 @@ EXPORTED_SYMBOLS = (
     "rt_camera_aspect_ratio", "rt_world_new", "rt_world_add_sphere", "rt_world_add_triangle",
     "rt_world_sphere_count", "rt_world_triangle_count", "rt_world_get_sphere", "rt_world_get_triangle",
     "rt_world_to_text", "rt_write_image", "rt_write_image_p6",
-    "rt_alloc_pixels", "rt_free_pixels", "rt_measure_fp32_peak", "rt_selftest_division",
+    "rt_alloc_pixels", "rt_free_pixels", "rt_measure_fp32_peak", "rt_selftest_division", "rt_selftest_sqrt",
     "rt_device_alloc", "rt_device_free", "rt_shard_block_bytes", "rt_shard_block_init", "rt_ipc_export", "rt_ipc_open", "rt_ipc_close", "rt_copy_to_host",
 )
 
@@ -201,6 +201,9 @@ def lib() -> C.CDLL:
     L.rt_ipc_close.argtypes = [C.c_void_p]
     L.rt_copy_to_host.restype = C.c_int
     L.rt_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    if not _variant or hasattr(L, "rt_selftest_sqrt"):
+        L.rt_selftest_sqrt.restype = C.c_longlong
+        L.rt_selftest_sqrt.argtypes = [C.c_int]
     L.rt_selftest_division.restype = C.c_longlong
     L.rt_selftest_division.argtypes = [C.c_int, C.c_ulonglong, C.c_uint32]
     _lib = L
@@ -527,6 +530,14 @@ def copy_to_host(host_ptr: int, device_ptr: int, nbytes: int, stream: int = 0) -
 def selftest_division(operand_sets: int = 1 << 28, seed: int = 1, device: int = -1) -> int:
     """Mismatches between the exact kernel's shared-reciprocal divide and the IEEE divide."""
     v = lib().rt_selftest_division(device, int(operand_sets), int(seed) & 0xFFFFFFFF)
+    if v < 0:
+        raise RenderError(last_error())
+    return v
+
+
+def selftest_sqrt(device: int = -1) -> int:
+    """Mismatches between the exact kernel's range-guarded square root and sqrtf over every float bit pattern."""
+    v = lib().rt_selftest_sqrt(device)
     if v < 0:
         raise RenderError(last_error())
     return v

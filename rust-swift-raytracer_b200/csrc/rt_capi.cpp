@@ -453,4 +453,11 @@ long long rt_selftest_division(int device, unsigned long long operand_sets, uint
     return v;
 }
 
+long long rt_selftest_sqrt(int device)
+{
+    long long v = -1;
+    guarded([&] { v = rt::selftest_sqrt(device); });
+    return v;
+}
+
 }   // extern "C"

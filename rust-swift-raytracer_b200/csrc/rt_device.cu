@@ -34,6 +34,7 @@ cudaError_t launch_resolve_samples_exact(const RtFrameParams&, cudaStream_t);
 cudaError_t launch_resolve_samples_fast(const RtFrameParams&, cudaStream_t);
 cudaError_t launch_selftest_division(unsigned long long n_per_thread, uint32_t seed, int grid, int block,
                                      unsigned long long* d_mismatches, cudaStream_t);
+cudaError_t launch_selftest_sqrt(int grid, int block, unsigned long long* d_mismatches, cudaStream_t);
 cudaError_t launch_ffma_peak(float* out, int iters, int grid, int block, cudaStream_t);
 double      ffma_peak_flops_per_launch(int iters, int grid, int block);
 
@@ -942,6 +943,23 @@ long long selftest_division(int device, unsigned long long operand_sets, uint32_
     RT_CUDA(cudaMalloc(&d, sizeof *d));
     RT_CUDA(cudaMemsetAsync(d, 0, sizeof *d, ctx.stream));
     RT_CUDA(launch_selftest_division(per_thread, seed, grid, block, d, ctx.stream));
+    unsigned long long h = 0;
+    RT_CUDA(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, ctx.stream));
+    RT_CUDA(cudaStreamSynchronize(ctx.stream));
+    RT_CUDA(cudaFree(d));
+    return (long long)h;
+}
+
+long long selftest_sqrt(int device)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    const int dev = resolve_device(device);
+    DeviceGuard guard(dev);
+    DeviceContext& ctx = context_for(dev);
+    unsigned long long* d = nullptr;
+    RT_CUDA(cudaMalloc(&d, sizeof *d));
+    RT_CUDA(cudaMemsetAsync(d, 0, sizeof *d, ctx.stream));
+    RT_CUDA(launch_selftest_sqrt(ctx.num_sms * 8, 256, d, ctx.stream));
     unsigned long long h = 0;
     RT_CUDA(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, ctx.stream));
     RT_CUDA(cudaStreamSynchronize(ctx.stream));

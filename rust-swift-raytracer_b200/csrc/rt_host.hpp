@@ -221,6 +221,9 @@ double measure_fp32_peak_tflops(int device, float* sm_clock_mhz_out);
 // GPU self-test of the shared-reciprocal divide against the compiler's IEEE divide on
 // `operand_sets` pseudo-random operand sets; returns the number of mismatching sets.
 long long selftest_division(int device, unsigned long long operand_sets, uint32_t seed);
+// GPU self-test of the range-guarded square root (rt_trace.cuh sqrt_ranged) against sqrtf on every float bit
+// pattern; returns the number of mismatching patterns.
+long long selftest_sqrt(int device);
 // Device memory that can be mapped into other processes (CUDA IPC): rank 0 owns the frame,
 // the other ranks' kernels store their tiles into it.  All throw std::runtime_error on failure.
 void* device_alloc(size_t bytes, int device = -1);   // -1: the current device

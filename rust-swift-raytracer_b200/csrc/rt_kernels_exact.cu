@@ -56,9 +56,9 @@ __global__ void rt_selftest_division_kernel(unsigned long long n_per_thread, uin
         float b = fabsf(v[3]);
         V3 q = div3<false>(a, b, false);
         bad += !(same_bits(q.x, a.x / b) && same_bits(q.y, a.y / b) && same_bits(q.z, a.z / b));
-        // the normalisation use (|a.c| <= len by construction)
+        // the normalisation (one range check for the root and the divides) against sqrtf and `/`
         float len = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
-        V3 nq = div3<false>(a, len, true);
+        V3 nq = normalize<false>(a);
         bad += !(same_bits(nq.x, a.x / len) && same_bits(nq.y, a.y / len) && same_bits(nq.z, a.z / len));
         // pixel_uv: (column + xi) / (W - 1)
         RtFrameParams P{};
@@ -70,6 +70,30 @@ __global__ void rt_selftest_division_kernel(unsigned long long n_per_thread, uin
         bad += !(same_bits(u, au / P.wm1) && same_bits(w, av / P.hm1));
     }
     if (bad) atomicAdd(mismatches, bad);
+}
+
+// Every float bit pattern from +0 to +inf and a few NaNs: where sqrt_in_range() holds, the bare sequence
+// sqrt_ranged() must give the bits of the compiler's IEEE sqrtf; the predicate itself must be exactly
+// 2^-100 <= x <= 2^100.  Counts the patterns that violate either.
+__global__ void rt_selftest_sqrt_kernel(unsigned long long* mismatches)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= 0x7f800010ull; b += stride) {
+        const float x = __uint_as_float((uint32_t)b);
+        const bool  in = sqrt_in_range(x);
+        bad += in != (x >= RT_SQRT_LO && x <= RT_SQRT_HI);
+        if (in) bad += !same_bits(sqrt_ranged(x), sqrtf(x));
+        const float nx = __uint_as_float((uint32_t)b | 0x80000000u);      // negatives never pass
+        bad += sqrt_in_range(nx);
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t launch_selftest_sqrt(int grid, int block, unsigned long long* d_mismatches, cudaStream_t stream)
+{
+    rt_selftest_sqrt_kernel<<<grid, block, 0, stream>>>(d_mismatches);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_selftest_division(unsigned long long n_per_thread, uint32_t seed, int grid, int block,

@@ -248,6 +248,11 @@ def test_shared_reciprocal_divide_equals_ieee_divide(gpu_rt):
         assert gpu_rt.selftest_division(1 << 29, seed) == 0
 
 
+def test_range_guarded_sqrt_equals_ieee_sqrt_for_every_float(gpu_rt):
+    """rt_trace.cuh sqrt_ranged / sqrt_in_range: all 2^31 non-negative bit patterns (and the negatives' predicate)."""
+    assert gpu_rt.selftest_sqrt() == 0
+
+
 # ------------------------------------------------------------------ progressive, shards, device API
 
 def test_progressive_passes_equal_one_pass(gpu_rt, ob, scenes):
