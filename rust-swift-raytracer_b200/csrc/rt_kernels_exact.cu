@@ -58,8 +58,9 @@ __global__ void rt_selftest_division_kernel(unsigned long long n_per_thread, uin
         bad += !(same_bits(q.x, a.x / b) && same_bits(q.y, a.y / b) && same_bits(q.z, a.z / b));
         // the normalisation (one range check for the root and the divides) against sqrtf and `/`
         float len = sqrtf(a.x * a.x + a.y * a.y + a.z * a.z);
-        V3 nq = normalize<false>(a);
+        V3 nq = normalize<false>(a), np = normalize<false, true>(a);
         bad += !(same_bits(nq.x, a.x / len) && same_bits(nq.y, a.y / len) && same_bits(nq.z, a.z / len));
+        bad += !(same_bits(np.x, a.x / len) && same_bits(np.y, a.y / len) && same_bits(np.z, a.z / len));
         // pixel_uv: (column + xi) / (W - 1)
         RtFrameParams P{};
         P.wm1 = (float)((m[0] % 8191u) + ((mode & 1u) ? 0u : 1u));       // includes 0 (1-pixel frame)
