@@ -57,13 +57,13 @@ WORKLOADS = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one render-kernel launch, from the committed
 # `ncu --set full` captures (profiles/r02_bench.md); None where no capture of that exact launch exists.
-NCU_TRAFFIC_BYTES = {("c2", False): 32768}      # 32.8 KB read, 0 B written: the 8.3 MB frame stays in the 126 MB L2
+NCU_TRAFFIC_BYTES = {("c2", False): 36352}      # 36.4 KB read, 0 B written: the 8.3 MB frame stays in the 126 MB L2
 # Counters of the same captures, quoted (not measured in this run) so that the line explains its own
 # `frac`: on the 8-sphere scene the counted-flops model covers less than half of the instructions a
 # segment needs (IEEE divide/sqrt sequences, integer RNG, predicates), and the kernel is issue-bound.
 NCU_CONTEXT = {
-    ("c2", False): {"issue_slots_busy": 0.866, "ipc": 3.42, "fp32_pipe_active": 0.459, "alu_pipe_active": 0.506,
-                    "active_lanes_per_warp": 19.8, "source": "profiles/r02_c2_exact_details.txt (16-spp capture)"},
+    ("c2", False): {"issue_slots_busy": 0.852, "ipc": 3.40, "fp32_pipe_active": 0.483, "alu_pipe_active": 0.502,
+                    "active_lanes_per_warp": 20.1, "source": "profiles/r02_c2_exact_details.txt (16-spp capture)"},
     ("c3", False): {"issue_slots_busy": 0.654, "ipc": 2.61, "fp32_pipe_active": 0.614, "active_lanes_per_warp": 29.8,
                     "source": "profiles/r02_c3_exact_details.txt (8-spp capture; FFMA2 filter: two FMAs per issued instruction)"},
     ("c5", False): {"issue_slots_busy": 0.640, "ipc": 2.37, "fp32_pipe_active": 0.475, "active_lanes_per_warp": 21.3,
