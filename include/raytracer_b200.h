@@ -97,6 +97,10 @@ typedef struct RtRenderOptions {
                                   in which the others are raided once this shard's own queue is empty. */
 } RtRenderOptions;
 
+/* Threading: like the reference (lib.rs is single-threaded, its callers block in render()), every render call of a
+ * process is serialised by one internal mutex, whatever device it targets; calls from several threads are safe and
+ * produce the frames they would produce alone.  The caller's current CUDA device is left as it was. */
+
 /* Thread-local text of the last failure of any call in this library ("" if none). */
 const char *rt_last_error(void);
 uint32_t    rt_abi_version(void);
