@@ -292,6 +292,9 @@ def main():
                     help="N > 1: 'peer' = render kernels store their tiles into rank 0's frame over NVLink "
                          "(CUDA IPC mapping); 'nccl' = compact buffers + one dist.gather")
     ap.add_argument("--no-steal", action="store_true", help="N > 1: static tile deal only (no cross-GPU work stealing)")
+    ap.add_argument("--no-row-gather", action="store_true",
+                    help="N > 1: every finished pixel is stored straight into rank 0's frame (one 4-byte store over NVLink) "
+                         "instead of being staged locally and copied across as 16-byte vectors by the launch's last CTA")
     ap.add_argument("--devices", type=int, default=0,
                     help="N = 1 launch only: also time render_with_options(n_devices=D), ONE process driving D GPUs "
                          "(the shape the C-ABI callers have); reported under e2e_one_process")
@@ -357,7 +360,7 @@ def main():
     S, T = handle.n_spheres, handle.n_triangles
     dev = torch.device("cuda", local_rank)
     renderer = multi.ShardedRenderer(rt, handle, W, H, rank, n_gpus, tile_rows=16, device=dev, gather=args.gather,
-                                     steal=not args.no_steal)
+                                     steal=not args.no_steal, row_gather=not args.no_row_gather)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -534,6 +537,7 @@ def main():
                        "api": "render_with_options(n_devices=D): one process, tiles stored into device 0's frame "
                               "over NVLink peer mappings, one D2H"}
     steal_on = bool(renderer.steal)
+    row_gather_on = bool(renderer.row_gather) and renderer.gather == "peer"
     gather = renderer.gather
     renderer.close()
     if rank != 0:
@@ -559,7 +563,9 @@ def main():
                    "parallelism": (f"row-tile shards x{n_gpus} (static boustrophedon deal"
                                    + (" + cross-GPU work stealing of the tail over NVLink atomics" if steal_on else "")
                                    + f"), {gather} gather to rank 0 "
-                                   + ("(fused into the render kernels: every finished pixel is stored into rank 0's frame over NVLink, CUDA IPC)"
+                                   + (("(fused into the render kernels: pixels staged in local memory, each kernel's last CTA copies its "
+                                       "shard's tiles into rank 0's frame over NVLink as 16-byte vectors, CUDA IPC)") if row_gather_on else
+                                      "(fused into the render kernels: every finished pixel is stored into rank 0's frame over NVLink, CUDA IPC)"
                                       if gather == "peer" else "(compact buffers + dist.gather)"))
                    if n_gpus > 1 else "1 GPU",
                    "stolen_slots_first_step": int(stolen_first) if n_gpus > 1 else 0,

@@ -42,6 +42,7 @@ OPT_SAMPLE_ITEMS = 0x80
 OPT_GROUP_CULL = 0x100
 OPT_RESOLVE_EACH_PASS = 0x200
 OPT_NO_STEAL = 0x400
+OPT_ROW_GATHER = 0x800
 DIFFUSE, METAL, DIELECTRIC, EMISSION = 0, 1, 2, 3   # materials.rs:7-12
 
 
@@ -247,12 +248,14 @@ class Options:
     resolve_each_pass: bool = False      # fused passes: refresh the RGBA8 frame after every pass
     peer_queues: Optional[list] = None   # [(block address, shard index), ...] of ALL shards: cross-GPU work stealing
     no_steal: bool = False               # with peer_queues: static tile deal only
+    row_gather: bool = False             # full_frame_out into ANOTHER GPU's frame: stage locally, last CTA copies 16-byte vectors
 
     def _c(self, stats: Optional[RenderStats]) -> _RenderOptions:
         flags = ((OPT_FIXED_JITTER if self.fixed_jitter else 0) | (OPT_FAST_MATH if self.fast_math else 0) |
                  (OPT_ACCUM_IN if self.accum_in else 0) | (OPT_ACCUM_OUT if self.accum_out else 0) |
                  (OPT_NO_RESOLVE if self.no_resolve else 0) | (OPT_FULL_FRAME_OUT if self.full_frame_out else 0) | (OPT_GROUP_CULL if self.group_cull else 0) |
                  (OPT_RESOLVE_EACH_PASS if self.resolve_each_pass else 0) | (OPT_NO_STEAL if self.no_steal else 0) |
+                 (OPT_ROW_GATHER if self.row_gather else 0) |
                  (0 if self.sample_items is None else OPT_SAMPLE_ITEMS if self.sample_items else OPT_PIXEL_ITEMS))
         o = _RenderOptions(C.sizeof(_RenderOptions), int(self.samples_per_pixel), int(self.max_ray_bounces),
                            int(self.seed) & 0xFFFFFFFF, flags, int(self.sample_begin), int(self.resolve_spp),

@@ -78,6 +78,7 @@ rt::Options to_options(const RtRenderOptions* o)
     r.peer_queues       = reinterpret_cast<const rt::PeerQueue*>(c.peer_queues);
     r.n_peer_queues     = c.peer_queues ? c.n_peer_queues : 0u;
     r.no_steal          = (c.flags & RT_OPT_NO_STEAL) != 0;
+    r.row_gather        = (c.flags & RT_OPT_ROW_GATHER) != 0;
     return r;
 }
 

@@ -49,10 +49,12 @@ namespace {
 constexpr int      kCounterSlots    = 64;
 constexpr uint64_t kSampleBufferCap = (uint64_t)1 << 30;
 
-struct CounterSlot {            // 16 B, zeroed by one memset per launch
+struct CounterSlot {            // 32 B, zeroed by one memset per launch
     unsigned long long rays;
     unsigned int       work;
     unsigned int       stolen;
+    unsigned int       cta_done;
+    unsigned int       pad[3];
 };
 
 // Shard block (cross-GPU work stealing): the shard's work counter, alone in its first 256 bytes, then
@@ -85,6 +87,7 @@ struct DeviceContext {
     RtFloat4*    d_samples = nullptr;  size_t d_samples_cap = 0; // per-sample colours of the sample-item mode
     RtFloat4*    d_accum = nullptr;    size_t d_accum_cap = 0;   // hand-over sums between sample-item chunks / fused passes
     unsigned char* d_block = nullptr;  size_t d_block_cap = 0;   // this device's shard block (ray_trace_multi)
+    uint32_t*    d_local_frame = nullptr; size_t d_local_cap = 0;  // row gather: this shard's pixels before they cross NVLink
     unsigned int* d_tile_done = nullptr; unsigned int* h_tile_flags = nullptr; size_t tile_cap = 0;   // tile completion
     uint32_t     tile_epoch = 0;
     struct Geometry { int per_sm = 0, block = 0, resident = 0, sph_mode = 0; size_t hot_bytes = 0; };
@@ -464,7 +467,22 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
         L.tile_flags = true;
     }
 
-    L.uses_scratch = L.sample_items || (P.accum && P.accum == ctx.d_accum) || (L.d_out && L.d_out == ctx.d_out);
+    // row gather: own pixels are staged in a local frame, the last CTA copies the shard's tiles to the remote frame
+    if (opt.row_gather && opt.full_frame_out && opt.shard_count > 1 && !L.sample_items && trace && !opt.no_resolve &&
+        !opt.resolve_each_pass && L.d_out && L.n_tiles > 0) {
+        const size_t px = (size_t)W * H;
+        if (ctx.d_local_cap < px) {
+            RT_CUDA(cudaStreamSynchronize(stream));
+            if (ctx.d_local_frame) RT_CUDA(cudaFree(ctx.d_local_frame));
+            ctx.d_local_frame = nullptr; ctx.d_local_cap = 0;
+            RT_CUDA(cudaMalloc(&ctx.d_local_frame, px * sizeof(uint32_t)));
+            ctx.d_local_cap = px;
+        }
+        RT_CUDA(cudaMemsetAsync(ctx.d_local_frame, 0, px * sizeof(uint32_t), stream));   // 0 = "not written here"
+        P.out_local = ctx.d_local_frame;
+        P.cta_done  = &L.slot->cta_done;
+    }
+    L.uses_scratch = L.sample_items || P.out_local != nullptr || (P.accum && P.accum == ctx.d_accum) || (L.d_out && L.d_out == ctx.d_out);
     if (L.n_tiles > 0 || stealing) {
         RT_CUDA(cudaMemsetAsync(L.slot, 0, sizeof(CounterSlot), stream));
         // fused passes: no stale sums may look like a finished pass.  Stream order puts this BEFORE the reset
@@ -810,6 +828,8 @@ void ray_trace_multi(const World& world, const Camera& camera, size_t width, siz
         RT_CUDA(cudaSetDevice(d));
         Options o = base;
         o.device = d; o.shard_index = (uint32_t)d; o.full_frame_out = peer;
+        static const bool row_gather_enabled = [] { const char* e = std::getenv("RT_ROW_GATHER"); return !(e && *e == '0'); }();
+        o.row_gather = peer && d > 0 && row_gather_enabled;    // device 0 writes its own memory
         if (steal) {                                   // raid order: the next device first, so that the thieves spread
             for (int i = 0; i < N; ++i) {
                 const int e = (d + i) % N;

@@ -103,7 +103,8 @@ class ShardedRenderer:
     """
 
     def __init__(self, rt, handle, width: int, height: int, rank: int = 0, world: int = 1,
-                 tile_rows: int = 16, device=None, gather: Optional[str] = None, steal: bool = True):
+                 tile_rows: int = 16, device=None, gather: Optional[str] = None, steal: bool = True,
+                 row_gather: bool = True):
         self.rt, self.handle = rt, handle
         self.width, self.height, self.rank, self.world, self.tile_rows = width, height, rank, world, tile_rows
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
@@ -117,6 +118,7 @@ class ShardedRenderer:
         self._peer_blocks = {}    # rank -> mapped address of its shard block
         self.queues = None        # [(block address, shard index)] own first, then (rank+1), (rank+2), ...
         self.steal = False        # cross-GPU work stealing is on
+        self.row_gather = bool(row_gather)   # ranks != 0 stage their pixels locally; their last CTA copies 16-byte vectors
         if self.gather == "peer" and world > 1:
             # Map rank 0's frame into every rank.  CUDA IPC can be unavailable (containers without a
             # shared IPC namespace, no peer access): all ranks then agree to use the NCCL gather — a
@@ -230,7 +232,8 @@ class ShardedRenderer:
         out_ptr = self.frame_ptr if peer else self.local.data_ptr()
         o = rt.Options(spp, depth, passes=passes, resolve_spp=spp, fast_math=fast_math, fixed_jitter=fixed_jitter,
                        tile_rows=self.tile_rows, shard_index=self.rank, shard_count=self.world,
-                       full_frame_out=peer, group_cull=group_cull, peer_queues=self.queues if self.steal else None)
+                       full_frame_out=peer, group_cull=group_cull, peer_queues=self.queues if self.steal else None,
+                       row_gather=peer and self.rank != 0 and self.row_gather)
         if seed is not None:
             o.seed = seed
         st = stats if stats is not None else (rt.RenderStats() if count_rays else None)

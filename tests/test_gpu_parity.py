@@ -687,6 +687,44 @@ def test_work_stealing_queues_on_one_gpu(gpu_rt, ob, scenes, passes):
     assert not got2[other].any()
 
 
+@pytest.mark.parametrize("passes", [1, 3])
+def test_row_gather_stages_locally_and_copies_vectorised(gpu_rt, ob, scenes, passes):
+    """RT_OPT_ROW_GATHER (what ranks != 0 use for a frame in rank 0's memory), on one device: the shard's own pixels go
+    to a local staging frame and the launch's LAST CTA copies its tiles into the destination as 16-byte vectors; pixels
+    the launch steals from other shards go straight to the destination, and zero words of the staging frame (pixels
+    somebody else traced) are skipped.  Ragged frame: 201 x 117, 8-row tiles (last tile 5 rows, rows of 804 bytes)."""
+    import torch
+    rt = gpu_rt
+    W, H, spp, depth = 201, 117, 6, 8
+    text = scenes.example_world()
+    h = rt.load_world(text)
+    cam, world = ob.parse_input(text)
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    # (a) three shards, each launched alone with row gather: together they fill the frame
+    out = torch.zeros((H, W), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    total = 0
+    for i in range(3):
+        st = rt.RenderStats()
+        rt.render_device(h, rt.Options(spp, depth, passes=passes, tile_rows=8, shard_index=i, shard_count=3,
+                                       full_frame_out=True, row_gather=True), W, H, out.data_ptr(), 0, 0, st)
+        total += st.rays
+    torch.cuda.synchronize()
+    assert total == rays and np.array_equal(out.cpu().numpy().view(np.uint8).reshape(H, W, 4), want)
+    # (b) shard 1 with row gather raids the queues of shards 2 and 0, whose owners never start: its own tiles arrive by
+    #     the vector copy, everything it stole by direct stores — and the copy must not wipe the stolen pixels
+    blocks = _blocks(rt, W, H, 3)
+    out = torch.full((H, W), 0x01020304, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    st = rt.RenderStats()
+    rt.render_device(h, rt.Options(spp, depth, passes=passes, tile_rows=8, shard_index=1, shard_count=3, full_frame_out=True,
+                                   row_gather=True, peer_queues=[(blocks[1].data_ptr(), 1), (blocks[2].data_ptr(), 2),
+                                                                 (blocks[0].data_ptr(), 0)]), W, H, out.data_ptr(), 0, 0, st)
+    torch.cuda.synchronize()
+    assert st.rays == rays and st.stolen_slots > 0
+    assert np.array_equal(out.cpu().numpy().view(np.uint8).reshape(H, W, 4), want)
+
+
 def test_work_stealing_rejects_bad_queue_tables(gpu_rt, scenes):
     import torch
     rt = gpu_rt
