@@ -294,7 +294,7 @@ def main():
     ap.add_argument("--no-steal", action="store_true", help="N > 1: static tile deal only (no cross-GPU work stealing)")
     ap.add_argument("--no-row-gather", action="store_true",
                     help="N > 1: every finished pixel is stored straight into rank 0's frame (one 4-byte store over NVLink) "
-                         "instead of being staged locally and copied across as 16-byte vectors by the launch's last CTA")
+                         "instead of being rendered into a local frame and copied across as 16-byte vectors by a second kernel")
     ap.add_argument("--devices", type=int, default=0,
                     help="N = 1 launch only: also time render_with_options(n_devices=D), ONE process driving D GPUs "
                          "(the shape the C-ABI callers have); reported under e2e_one_process")
@@ -563,8 +563,8 @@ def main():
                    "parallelism": (f"row-tile shards x{n_gpus} (static boustrophedon deal"
                                    + (" + cross-GPU work stealing of the tail over NVLink atomics" if steal_on else "")
                                    + f"), {gather} gather to rank 0 "
-                                   + (("(fused into the render kernels: pixels staged in local memory, each kernel's last CTA copies its "
-                                       "shard's tiles into rank 0's frame over NVLink as 16-byte vectors, CUDA IPC)") if row_gather_on else
+                                   + (("(ranks != 0 render into a local frame; a copy kernel on the same stream moves their pixels into rank 0's "
+                                       "frame over NVLink as 16-byte vectors, CUDA IPC)") if row_gather_on else
                                       "(fused into the render kernels: every finished pixel is stored into rank 0's frame over NVLink, CUDA IPC)"
                                       if gather == "peer" else "(compact buffers + dist.gather)"))
                    if n_gpus > 1 else "1 GPU",

@@ -31,8 +31,9 @@ extern "C" {
 #define RT_OPT_RESOLVE_EACH_PASS 0x200u /* passes > 1: refresh the RGBA8 frame after every pass, not only the last */
 #define RT_OPT_NO_STEAL      0x400u /* peer_queues given: no cross-GPU work stealing (static tile deal only) */
 #define RT_OPT_ROW_GATHER    0x800u /* rt_render_device with RT_OPT_FULL_FRAME_OUT when device_pixels is a frame in ANOTHER
-                                       GPU's memory: this shard's pixels are staged in local memory and copied across by the
-                                       launch's last CTA as 16-byte vectors, instead of one 4-byte store per pixel over NVLink */
+                                       GPU's memory: the shard is rendered into a local, zeroed frame and a small second kernel
+                                       moves every pixel found there across as 16-byte vectors, instead of one 4-byte store
+                                       per pixel over NVLink.  (A zero word means "not rendered here": alpha is always 255.) */
 #define RT_OPT_FULL_FRAME_OUT 0x20u /* rt_render_device with shard_count > 1: device_pixels / device_accum are
                                        FULL width*height frames (e.g. another GPU's frame mapped through CUDA IPC
                                        or peer access); this shard's tiles are stored at their frame offsets */

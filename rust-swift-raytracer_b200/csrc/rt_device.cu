@@ -35,6 +35,7 @@ cudaError_t launch_resolve_samples_fast(const RtFrameParams&, cudaStream_t);
 cudaError_t launch_selftest_division(unsigned long long n_per_thread, uint32_t seed, int grid, int block,
                                      unsigned long long* d_mismatches, cudaStream_t);
 cudaError_t launch_selftest_sqrt(int grid, int block, unsigned long long* d_mismatches, cudaStream_t);
+cudaError_t launch_gather_rows(const uint32_t* local, uint32_t* remote, size_t n_pixels, int grid, cudaStream_t);
 cudaError_t launch_ffma_peak(float* out, int iters, int grid, int block, cudaStream_t);
 double      ffma_peak_flops_per_launch(int iters, int grid, int block);
 
@@ -49,12 +50,10 @@ namespace {
 constexpr int      kCounterSlots    = 64;
 constexpr uint64_t kSampleBufferCap = (uint64_t)1 << 30;
 
-struct CounterSlot {            // 32 B, zeroed by one memset per launch
+struct CounterSlot {            // 16 B, zeroed by one memset per launch
     unsigned long long rays;
     unsigned int       work;
     unsigned int       stolen;
-    unsigned int       cta_done;
-    unsigned int       pad[3];
 };
 
 // Shard block (cross-GPU work stealing): the shard's work counter, alone in its first 256 bytes, then
@@ -467,9 +466,11 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
         L.tile_flags = true;
     }
 
-    // row gather: own pixels are staged in a local frame, the last CTA copies the shard's tiles to the remote frame
+    // Row gather: the frame lives in another GPU's memory.  Render into a local, zeroed full frame with the very same
+    // kernel, then one small kernel moves every pixel found there across NVLink as 16-byte vectors (rt_gather_rows_kernel).
+    uint32_t* gather_remote = nullptr;
     if (opt.row_gather && opt.full_frame_out && opt.shard_count > 1 && !L.sample_items && trace && !opt.no_resolve &&
-        !opt.resolve_each_pass && L.d_out && L.n_tiles > 0) {
+        !opt.resolve_each_pass && L.d_out && (L.n_tiles > 0 || stealing)) {
         const size_t px = (size_t)W * H;
         if (ctx.d_local_cap < px) {
             RT_CUDA(cudaStreamSynchronize(stream));
@@ -478,11 +479,11 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
             RT_CUDA(cudaMalloc(&ctx.d_local_frame, px * sizeof(uint32_t)));
             ctx.d_local_cap = px;
         }
-        RT_CUDA(cudaMemsetAsync(ctx.d_local_frame, 0, px * sizeof(uint32_t), stream));   // 0 = "not written here"
-        P.out_local = ctx.d_local_frame;
-        P.cta_done  = &L.slot->cta_done;
+        RT_CUDA(cudaMemsetAsync(ctx.d_local_frame, 0, px * sizeof(uint32_t), stream));   // 0 = "not rendered here"
+        gather_remote = L.d_out;
+        P.out         = ctx.d_local_frame;
     }
-    L.uses_scratch = L.sample_items || P.out_local != nullptr || (P.accum && P.accum == ctx.d_accum) || (L.d_out && L.d_out == ctx.d_out);
+    L.uses_scratch = L.sample_items || gather_remote != nullptr || (P.accum && P.accum == ctx.d_accum) || (L.d_out && L.d_out == ctx.d_out);
     if (L.n_tiles > 0 || stealing) {
         RT_CUDA(cudaMemsetAsync(L.slot, 0, sizeof(CounterSlot), stream));
         // fused passes: no stale sums may look like a finished pass.  Stream order puts this BEFORE the reset
@@ -494,6 +495,10 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
             RT_CUDA(opt.fast_math ? launch_render_fast(P, scene.view, L.grid, L.smem_limit, stream)
                                   : launch_render_exact(P, scene.view, L.grid, L.smem_limit, stream));
             L.launches = 1;
+            if (gather_remote) {
+                RT_CUDA(launch_gather_rows(ctx.d_local_frame, gather_remote, (size_t)W * H, ctx.num_sms * 4, stream));
+                L.launches = 2;
+            }
         } else {
             // sample items: [trace chunk_spp samples -> ordered sum] per chunk, sums handed on in P.accum
             const uint32_t user_flags = P.flags;

@@ -139,9 +139,9 @@ struct Options {
     const PeerQueue* peer_queues   = nullptr;
     uint32_t         n_peer_queues = 0;
     bool     no_steal       = false;        // peer_queues given, but every GPU traces only its own shard
-    // device_pixels is a full frame in ANOTHER GPU's memory (peer access / CUDA IPC): stage this shard's own pixels in a
-    // local frame and let the launch's last CTA copy its tiles across as 16-byte vectors, instead of one 4-byte store
-    // per pixel over NVLink (rt_types.h, "row gather").  Needs full_frame_out and whole-pixel items.
+    // device_pixels is a full frame in ANOTHER GPU's memory (peer access / CUDA IPC): render into a local, zeroed frame
+    // with the same kernel and let a small second kernel move every pixel found there across as 16-byte vectors,
+    // instead of one 4-byte store per pixel over NVLink ("row gather").  Needs full_frame_out and whole-pixel items.
     bool     row_gather     = false;
     RenderStats* stats      = nullptr;
 };

@@ -353,12 +353,8 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
                 if (!last || (P.flags & RT_FLAG_ACCUM_OUT))
                     accum_store(&ac[Lp.out_index], make_float4(Lp.acc_r, Lp.acc_g, Lp.acc_b, acc_a));
                 if (last ? !(P.flags & RT_FLAG_NO_RESOLVE) : (P.flags & RT_FLAG_RESOLVE_EACH_PASS) != 0u) {
-                {
-                    // own pixels of a shard whose frame is remote are staged locally (row gather, below)
-                    uint32_t* frame = (P.out_local && !(Lp.ctl & 0x00ff0000u)) ? P.out_local : P.out;
-                    frame[Lp.out_index] = resolve_pixel<FAST>(Lp.acc_r, Lp.acc_g, Lp.acc_b, acc_a,
+                    P.out[Lp.out_index] = resolve_pixel<FAST>(Lp.acc_r, Lp.acc_g, Lp.acc_b, acc_a,
                                                               last ? P.resolve_spp : P.sample_begin + pass_end);
-                }
                 }
                 if (last && P.tile_done) {      // full-frame output: out_index = image_row * width + column
                     const uint32_t tile  = (Lp.out_index / P.width) / P.tile_rows;
@@ -380,44 +376,6 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) segs += __shfl_xor_sync(FULL, segs, o);
     if (lane == 0 && P.ray_counter && segs) atomicAdd(P.ray_counter, segs);
-
-    // ---- row gather: the last CTA to get here copies the shard's tiles to the (remote) frame, vectorised ----
-    if (P.out_local) {
-        __shared__ unsigned int rt_is_last;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();                                           // this CTA's pixels before its count
-            rt_is_last = (atomicAdd(P.cta_done, 1u) + 1u == gridDim.x) ? 1u : 0u;
-        }
-        __syncthreads();
-        if (rt_is_last) {
-            __threadfence();                                           // every other CTA's pixels after their counts
-            for (uint32_t j = 0; j < P.n_tiles; ++j) {
-                const uint32_t tile  = rt_shard_tile(P.tile_first, P.tile_stride, j);
-                const uint32_t first = tile * P.tile_rows * P.width;   // a multiple of 4 pixels (tile_rows is)
-                const uint32_t rows  = min((tile + 1u) * P.tile_rows, P.height) - tile * P.tile_rows;
-                const uint32_t n     = rows * P.width, n4 = n >> 2;
-                const uint4*   src4  = reinterpret_cast<const uint4*>(P.out_local + first);
-                uint4*         dst4  = reinterpret_cast<uint4*>(P.out + first);
-                for (uint32_t i = threadIdx.x; i < n4; i += BLOCK) {
-                    const uint4 v = __ldcg(src4 + i);                  // L2: other SMs wrote these words
-                    if (v.x && v.y && v.z && v.w) {
-                        dst4[i] = v;
-                    } else {                                           // some of the four were traced by another GPU
-                        uint32_t* d = reinterpret_cast<uint32_t*>(dst4 + i);
-                        if (v.x) d[0] = v.x;
-                        if (v.y) d[1] = v.y;
-                        if (v.z) d[2] = v.z;
-                        if (v.w) d[3] = v.w;
-                    }
-                }
-                for (uint32_t i = (n4 << 2) + threadIdx.x; i < n; i += BLOCK) {
-                    const uint32_t v = __ldcg(P.out_local + first + i);
-                    if (v) P.out[first + i] = v;
-                }
-            }
-        }
-    }
 }
 
 // Second kernel of the RT_FLAG_SAMPLE_ITEMS mode: one thread per pixel adds the pixel's sample

@@ -91,6 +91,40 @@ __global__ void rt_selftest_sqrt_kernel(unsigned long long* mismatches)
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// Row gather (multi-GPU): a GPU whose frame lives in ANOTHER GPU's memory renders into a local, zeroed, full-frame
+// buffer — the render kernel is exactly the single-GPU one — and this kernel then moves every pixel it finds there
+// (its own tiles and whatever it stole from other shards) into the remote frame: 16-byte vector stores wherever four
+// neighbouring pixels are all present (512 contiguous bytes per warp and step over NVLink instead of one 4-byte store per
+// pixel), word by word at the ragged edges.  A zero word means "not rendered here": every real pixel has alpha 255.
+__global__ void __launch_bounds__(256) rt_gather_rows_kernel(const uint32_t* __restrict__ local, uint32_t* __restrict__ remote,
+                                                             size_t n_pixels)
+{
+    const size_t  n4 = n_pixels >> 2, stride = (size_t)gridDim.x * blockDim.x;
+    const uint4*  src4 = reinterpret_cast<const uint4*>(local);
+    uint4*        dst4 = reinterpret_cast<uint4*>(remote);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const uint4 v = src4[i];
+        if (!(v.x | v.y | v.z | v.w)) continue;
+        if (v.x && v.y && v.z && v.w) {
+            dst4[i] = v;
+        } else {
+            uint32_t* d = reinterpret_cast<uint32_t*>(dst4 + i);
+            if (v.x) d[0] = v.x;
+            if (v.y) d[1] = v.y;
+            if (v.z) d[2] = v.z;
+            if (v.w) d[3] = v.w;
+        }
+    }
+    for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pixels; i += stride)
+        if (local[i]) remote[i] = local[i];
+}
+
+cudaError_t launch_gather_rows(const uint32_t* local, uint32_t* remote, size_t n_pixels, int grid, cudaStream_t stream)
+{
+    rt_gather_rows_kernel<<<grid, 256, 0, stream>>>(local, remote, n_pixels);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_selftest_sqrt(int grid, int block, unsigned long long* d_mismatches, cudaStream_t stream)
 {
     rt_selftest_sqrt_kernel<<<grid, block, 0, stream>>>(d_mismatches);

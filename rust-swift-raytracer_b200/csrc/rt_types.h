@@ -185,14 +185,6 @@ struct RtFrameParams {
     unsigned int* tile_flags;
     uint32_t  tile_epoch;
     uint32_t  pad_tile;
-    // Row gather (multi-GPU, `out` is a frame in ANOTHER GPU's memory): this shard's own pixels are stored into
-    // out_local — a full-frame-indexed buffer in local memory, zeroed before the launch — and the last CTA of the launch
-    // to finish copies the shard's tiles to `out` as 16-byte vectors (512 contiguous bytes per warp and step).  Pixels the
-    // launch STOLE from other shards go straight to `out`, 4 bytes each.  A zero word in out_local is "not written
-    // here" (a pixel's alpha byte is always 255): the copy skips it, so pixels of this shard that another GPU stole —
-    // and wrote into `out` itself — are never overwritten.
-    uint32_t*     out_local;
-    unsigned int* cta_done;      // CTAs of this launch that have left the render loop (zeroed before the launch)
     uint32_t  n_queues;      // >= 1
     RtQueue   queues[RT_MAX_QUEUES];   // [0] = the launch's own shard (work_counter / accum above), then the peers
 };

@@ -118,7 +118,7 @@ class ShardedRenderer:
         self._peer_blocks = {}    # rank -> mapped address of its shard block
         self.queues = None        # [(block address, shard index)] own first, then (rank+1), (rank+2), ...
         self.steal = False        # cross-GPU work stealing is on
-        self.row_gather = bool(row_gather)   # ranks != 0 stage their pixels locally; their last CTA copies 16-byte vectors
+        self.row_gather = bool(row_gather)   # ranks != 0 render into a local frame; a copy kernel moves it over as 16-byte vectors
         if self.gather == "peer" and world > 1:
             # Map rank 0's frame into every rank.  CUDA IPC can be unavailable (containers without a
             # shared IPC namespace, no peer access): all ranks then agree to use the NCCL gather — a

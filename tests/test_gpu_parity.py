@@ -689,10 +689,10 @@ def test_work_stealing_queues_on_one_gpu(gpu_rt, ob, scenes, passes):
 
 @pytest.mark.parametrize("passes", [1, 3])
 def test_row_gather_stages_locally_and_copies_vectorised(gpu_rt, ob, scenes, passes):
-    """RT_OPT_ROW_GATHER (what ranks != 0 use for a frame in rank 0's memory), on one device: the shard's own pixels go
-    to a local staging frame and the launch's LAST CTA copies its tiles into the destination as 16-byte vectors; pixels
-    the launch steals from other shards go straight to the destination, and zero words of the staging frame (pixels
-    somebody else traced) are skipped.  Ragged frame: 201 x 117, 8-row tiles (last tile 5 rows, rows of 804 bytes)."""
+    """RT_OPT_ROW_GATHER (what ranks != 0 use for a frame in rank 0's memory), on one device: the launch renders into a
+    local, zeroed frame and a second kernel moves every pixel found there into the destination as 16-byte vectors —
+    its own tiles and whatever it stole — skipping zero words (pixels somebody else traced), so nothing already in the
+    destination is wiped.  Ragged frame: 201 x 117, 8-row tiles (last tile 5 rows, rows of 804 bytes)."""
     import torch
     rt = gpu_rt
     W, H, spp, depth = 201, 117, 6, 8
@@ -711,8 +711,8 @@ def test_row_gather_stages_locally_and_copies_vectorised(gpu_rt, ob, scenes, pas
         total += st.rays
     torch.cuda.synchronize()
     assert total == rays and np.array_equal(out.cpu().numpy().view(np.uint8).reshape(H, W, 4), want)
-    # (b) shard 1 with row gather raids the queues of shards 2 and 0, whose owners never start: its own tiles arrive by
-    #     the vector copy, everything it stole by direct stores — and the copy must not wipe the stolen pixels
+    # (b) shard 1 with row gather raids the queues of shards 2 and 0, whose owners never start: own and stolen pixels
+    #     all arrive by the vector copy
     blocks = _blocks(rt, W, H, 3)
     out = torch.full((H, W), 0x01020304, dtype=torch.int32, device="cuda")
     torch.cuda.synchronize()
@@ -791,7 +791,8 @@ def test_one_process_many_gpus_peer_store_gather(gpu_rt, ob, scenes):
         for pinned in (False, True):
             got, st = _render(rt, h, W, H, 4, 8, pinned=pinned, n_devices=nd)
             assert np.array_equal(got, full), (nd, pinned)
-            assert st.devices == nd and st.rays == st1.rays and st.launches == nd and st.peer_gather == 1
+            # one render kernel per device + one row-gather copy kernel on every device but the one that owns the frame
+            assert st.devices == nd and st.rays == st1.rays and st.launches == 2 * nd - 1 and st.peer_gather == 1
 
 
 def _dist_worker(rank, world, port, gather, q):
