@@ -389,6 +389,7 @@ def main():
     _, rays_local = renderer.render(spp, depth, passes, fast_math=fast, count_rays=True, group_cull=args.cull, stats=st0)
     rays_frame = allreduce(float(rays_local), dist.ReduceOp.SUM if n_gpus > 1 else None)
     stolen_first = allreduce(float(st0.stolen_slots), dist.ReduceOp.SUM if n_gpus > 1 else None)
+    launches_all = allreduce(float(st0.launches), dist.ReduceOp.SUM if n_gpus > 1 else None)   # kernels per step, all ranks
     for _ in range(max(args.warmup - 1, 0)):
         flush.zero_()
         renderer.render(spp, depth, passes, fast_math=fast, group_cull=args.cull)
@@ -548,7 +549,6 @@ def main():
     samples = W * H * spp
     flops = algorithmic_flops(rays_frame, samples, W * H, S, T)
     achieved = flops / (ms_per_step * 1e-3) / 1e12
-    launches_per_step = int(st0.launches)
     line = {
         "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -574,7 +574,7 @@ def main():
                    "frame_sha256": frame_sha,
                    },
         "e2e": e2e,
-        "gpu_launches": args.steps * launches_per_step * n_gpus,
+        "gpu_launches": args.steps * int(launches_all),     # render kernels (+ the row-gather copy kernel on ranks != 0)
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak * n_gpus, "unit": "TFLOP/s",
                      "frac": achieved / (fp32_peak * n_gpus) if fp32_peak else None,
                      "traffic": NCU_TRAFFIC_BYTES.get((args.workload, fast)) if (n_gpus == 1 and not args.spp) else None,
