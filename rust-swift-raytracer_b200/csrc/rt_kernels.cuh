@@ -38,9 +38,7 @@ __host__ __device__ inline uint32_t rt_hot_bytes(const RtSceneView& G, int sph_m
 {
     if (sph_mode == RT_SPH_CULL) return (10u * G.n_groups + G.n_tri_pad) * (uint32_t)sizeof(RtFloat4);
     uint32_t b = (G.n_sph_pad + G.n_tri_pad) * (uint32_t)sizeof(RtFloat4);
-#if !defined(RT_R2_GLOBAL)
     if (sph_mode == RT_SPH_FILTER) b += ((G.n_sph_pad * (uint32_t)sizeof(float)) + 15u) & ~15u;
-#endif
     return b;
 }
 
@@ -191,11 +189,7 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
         } else {
             sph       = reinterpret_cast<const RtFloat4*>(rt_smem);
             tri_plane = sph + G.n_sph_pad;
-#if defined(RT_R2_GLOBAL)
-            if (SPH == RT_SPH_FILTER) sph_r2 = G.sph_r2;       // survivors only: left in global memory, L1 keeps more of the cull records
-#else
             if (SPH == RT_SPH_FILTER) sph_r2 = reinterpret_cast<const float*>(tri_plane + G.n_tri_pad);
-#endif
         }
     } else {
         sph       = SPH == RT_SPH_FILTER ? G.sph_filter : G.sph;
