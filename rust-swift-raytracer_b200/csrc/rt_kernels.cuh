@@ -181,13 +181,20 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
         const void*    src       = SPH == RT_SPH_CULL ? (const void*)G.cull_bound
                                  : SPH == RT_SPH_FILTER ? (const void*)G.sph_filter : (const void*)G.sph;
         if (hot_bytes) stage_scene_tma(rt_smem, src, hot_bytes, &rt_mbar);
+        // The staged lists are addressed from ONE opaque copy of the block's shared-memory address.  Left to itself the
+        // compiler treats `&rt_smem` as a free constant and re-derives it (S2UR SR_CgaCtaId, UMOV, UIADD3, ULEA) in
+        // every iteration of the intersection loops — 6 of the 55 instructions of a FILTER group; through the opaque
+        // value it stays in one uniform register and the loads become LDS [R + UR + imm].
+        uint32_t hot_base = smem_u32(rt_smem);
+        asm volatile("" : "+r"(hot_base));
+        const RtFloat4* const hot = reinterpret_cast<const RtFloat4*>(__cvta_shared_to_generic(hot_base));
         if (SPH == RT_SPH_CULL) {
-            cv.bound  = reinterpret_cast<const RtFloat4*>(rt_smem);
+            cv.bound  = hot;
             cv.sph9   = cv.bound + G.n_groups;
             sph       = cv.sph9;                               // not walked in list order in this mode
             tri_plane = cv.sph9 + 9u * G.n_groups;
         } else {
-            sph       = reinterpret_cast<const RtFloat4*>(rt_smem);
+            sph       = hot;
             tri_plane = sph + G.n_sph_pad;
             if (SPH == RT_SPH_FILTER) sph_r2 = reinterpret_cast<const float*>(tri_plane + G.n_tri_pad);
         }
