@@ -410,7 +410,7 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
     if ((uint64_t)slots * P.passes >= 0x7fffff00ull) throw std::runtime_error("frame shard exceeds 2^31 work slots; use more shards or fewer passes");
 
     // launch geometry: persistent CTAs, resident-CTA count from the occupancy API
-    L.smem_limit = ctx.smem_optin > 256 ? ctx.smem_optin - 256 : 0;     // static smem: the mbarrier + alignment (128 B)
+    L.smem_limit = ctx.smem_optin > 1024 ? ctx.smem_optin - 1024 : 0;   // static smem: the mbarrier
     auto& occ    = ctx.occupancy[{scene.view.n_sph_pad, scene.view.n_tri_pad, scene.view.n_groups, opt.fast_math ? 1 : 0,
                                   opt.group_cull ? 1 : 0}];
     if (occ.per_sm == 0) {

@@ -161,7 +161,7 @@ struct World {
     // packed host copy of the scene blob (rt_types.h layout), built on demand
     struct Packed {
         std::vector<unsigned char> blob;
-        size_t off_sph = 0, off_tri_plane = 0, off_sph_filter = 0, off_sph_r2 = 0, off_tri_edge = 0, off_tri_k = 0, off_tri_v = 0,
+        size_t off_sph = 0, off_tri_plane = 0, off_sph_filter = 0, off_sph_r2 = 0, off_tri_cull = 0, off_tri_v = 0,
                off_info = 0, off_cull_bound = 0, off_cull_sph = 0, off_cull_r2 = 0, off_cull_orig = 0;
         uint32_t n_sph = 0, n_sph_pad = 0, n_tri = 0, n_tri_pad = 0, n_groups = 0;
         RtSceneView view(const unsigned char* base) const;

@@ -33,26 +33,13 @@
 
 namespace rt {
 
-// What a CTA stages in shared memory.  DIRECT: block A {sph | tri_plane}.  CULL: block C {cull_bound | cull_sph |
-// tri_plane}.  FILTER: the lists {sph_filter | tri_plane} of block B and behind them, as RtSceneView::hot_parts says,
-// the edge-stage records of the triangles, their K, and the exact r*r of the spheres — each read from the blob in
-// global memory when it is not staged.
-struct HotPlan { uint32_t lists, edge, k, r2; };
-__host__ __device__ inline HotPlan rt_hot_plan(const RtSceneView& G, int sph_mode, uint32_t parts)
+// bytes of the hot lists a CTA stages (block A or block B of rt_types.h)
+__host__ __device__ inline uint32_t rt_hot_bytes(const RtSceneView& G, int sph_mode)
 {
-    HotPlan h{0u, 0u, 0u, 0u};
-    if (sph_mode == RT_SPH_CULL) { h.lists = (10u * G.n_groups + G.n_tri_pad) * (uint32_t)sizeof(RtFloat4); return h; }
-    h.lists = (G.n_sph_pad + G.n_tri_pad) * (uint32_t)sizeof(RtFloat4);
-    if (sph_mode != RT_SPH_FILTER) return h;
-    if (parts & RT_HOT_EDGE) h.edge = G.n_tri_pad * 2u * (uint32_t)sizeof(RtFloat4);          // 4 float4 per pair
-    if (parts & RT_HOT_K)    h.k    = ((G.n_tri_pad * (uint32_t)sizeof(float)) + 15u) & ~15u;
-    if (parts & RT_HOT_R2)   h.r2   = ((G.n_sph_pad * (uint32_t)sizeof(float)) + 15u) & ~15u;
-    return h;
-}
-__host__ __device__ inline uint32_t rt_hot_bytes(const RtSceneView& G, int sph_mode, uint32_t parts)
-{
-    const HotPlan h = rt_hot_plan(G, sph_mode, parts);
-    return h.lists + h.edge + h.k + h.r2;
+    if (sph_mode == RT_SPH_CULL) return (10u * G.n_groups + G.n_tri_pad) * (uint32_t)sizeof(RtFloat4);
+    uint32_t b = (G.n_sph_pad + G.n_tri_pad) * (uint32_t)sizeof(RtFloat4);
+    if (sph_mode == RT_SPH_FILTER) b += ((G.n_sph_pad * (uint32_t)sizeof(float)) + 15u) & ~15u;
+    return b;
 }
 
 // --- TMA bulk copy (global -> shared) of the hot primitive list -------------------------
@@ -61,10 +48,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p)
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
-struct HotSegment { const void* src; uint32_t bytes; };      // bytes: a multiple of 16
-
-template <int N>
-__device__ __forceinline__ void stage_scene_tma(void* smem_dst, const HotSegment (&seg)[N], unsigned long long* mbar)
+__device__ __forceinline__ void stage_scene_tma(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                                unsigned long long* mbar)
 {
     const uint32_t bar = smem_u32(mbar);
     if (threadIdx.x == 0) {
@@ -73,26 +58,19 @@ __device__ __forceinline__ void stage_scene_tma(void* smem_dst, const HotSegment
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t total = 0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) total += seg[i].bytes;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                      : "memory");
         uint32_t       dst = smem_u32(smem_dst);
+        const char*    src = static_cast<const char*>(gmem_src);
+        uint32_t       off = 0;
         const uint32_t CH  = 32768u;   // keep each bulk copy modest; all complete on one barrier
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const char* src = static_cast<const char*>(seg[i].src);
-            uint32_t    off = 0;
-            while (off < seg[i].bytes) {
-                uint32_t n = seg[i].bytes - off < CH ? seg[i].bytes - off : CH;
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                    ::"r"(dst + off), "l"(src + off), "r"(n), "r"(bar)
-                    : "memory");
-                off += n;
-            }
-            dst += seg[i].bytes;
+        while (off < bytes) {
+            uint32_t n = bytes - off < CH ? bytes - off : CH;
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                ::"r"(dst + off), "l"(src + off), "r"(n), "r"(bar)
+                : "memory");
+            off += n;
         }
     }
     uint32_t done = 0;
@@ -196,16 +174,13 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
     // {cull_bound | cull_sph | tri_plane} of rt_types.h — each one contiguous range of the scene blob
     const RtFloat4* sph;
     const RtFloat4* tri_plane;
-    const float*    sph_r2   = SPH == RT_SPH_FILTER ? G.sph_r2 : nullptr;
-    const RtFloat4* tri_edge = G.tri_edge;
-    const float*    tri_k    = G.tri_k;
+    const float*    sph_r2 = nullptr;
     CullView        cv{G.cull_bound, G.cull_sph, G.cull_r2, G.cull_orig, G.n_groups};
     if (SMEM) {
-        const HotPlan     hp     = rt_hot_plan(G, SPH, G.hot_parts);
-        const HotSegment  seg[4] = {{SPH == RT_SPH_CULL ? (const void*)G.cull_bound
-                                     : SPH == RT_SPH_FILTER ? (const void*)G.sph_filter : (const void*)G.sph, hp.lists},
-                                    {G.tri_edge, hp.edge}, {G.tri_k, hp.k}, {G.sph_r2, hp.r2}};
-        if (hp.lists) stage_scene_tma(rt_smem, seg, &rt_mbar);
+        const uint32_t hot_bytes = rt_hot_bytes(G, SPH);
+        const void*    src       = SPH == RT_SPH_CULL ? (const void*)G.cull_bound
+                                 : SPH == RT_SPH_FILTER ? (const void*)G.sph_filter : (const void*)G.sph;
+        if (hot_bytes) stage_scene_tma(rt_smem, src, hot_bytes, &rt_mbar);
         // The staged lists are addressed from ONE opaque copy of the block's shared-memory address.  Left to itself the
         // compiler treats `&rt_smem` as a free constant and re-derives it (S2UR SR_CgaCtaId, UMOV, UIADD3, ULEA) in
         // every iteration of the intersection loops — 6 of the 55 instructions of a FILTER group; through the opaque
@@ -221,18 +196,12 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
         } else {
             sph       = hot;
             tri_plane = sph + G.n_sph_pad;
-            if (SPH == RT_SPH_FILTER) {                        // optional parts: staged, or left in the blob
-                const unsigned char* part = reinterpret_cast<const unsigned char*>(hot) + hp.lists;
-                if (hp.edge) tri_edge = reinterpret_cast<const RtFloat4*>(part);
-                part += hp.edge;
-                if (hp.k) tri_k = reinterpret_cast<const float*>(part);
-                part += hp.k;
-                if (hp.r2) sph_r2 = reinterpret_cast<const float*>(part);
-            }
+            if (SPH == RT_SPH_FILTER) sph_r2 = reinterpret_cast<const float*>(tri_plane + G.n_tri_pad);
         }
     } else {
         sph       = SPH == RT_SPH_FILTER ? G.sph_filter : G.sph;
         tri_plane = G.tri_plane;
+        if (SPH == RT_SPH_FILTER) sph_r2 = G.sph_r2;
     }
 
     const uint32_t FULL = 0xffffffffu;
@@ -340,7 +309,7 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
         if (NP == 1) {
             sample_done[0] = false;
             if (ready[0] && trace) {
-                sample_done[0] = trace_segment<FAST, SPH, TRIS>(L[0], P, G, sph, sph_r2, cv, tri_plane, tri_edge, tri_k);
+                sample_done[0] = trace_segment<FAST, SPH, TRIS>(L[0], P, G, sph, sph_r2, cv, tri_plane);
                 ++segments;
             }
         } else {
@@ -360,7 +329,7 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
                 }
             }
             if (live) {
-                closest_hit_n<FAST, TRIS, NP>(sph, sph_r2, G.n_sph, G.n_sph_pad, tri_plane, tri_edge, tri_k, G.tri_v, G.n_tri_pad, o, d, P.one, h);
+                closest_hit_n<FAST, TRIS, NP>(sph, sph_r2, G.n_sph, G.n_sph_pad, tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, P.one, h);
 #pragma unroll
                 for (int p = 0; p < NP; ++p)
                     if (ready[p] && trace) sample_done[p] = segment_end<FAST, SPH, TRIS>(L[p], G, sph, d[p], h[p]);
@@ -468,7 +437,7 @@ constexpr int      kBlockLarge2   = RT_BLOCK_LARGE / 2;   // two paths per lane:
 constexpr size_t   kLargeSmemFrom = 56 * 1024;   // above this, < 4 CTAs of 256 threads would fit
 constexpr uint32_t kFilterFrom    = RT_FILTER_FROM;   // spheres from which the kernels filter first
 
-struct RenderVariant { bool smem; int block; int sph; bool tris; size_t hot_bytes; int np; uint32_t parts; };
+struct RenderVariant { bool smem; int block; int sph; bool tris; size_t hot_bytes; int np; };
 
 // Paths per lane of the FILTER kernels.  Measured with the FFMA2 filter (profiles/r02_bench.md): one path per lane
 // is as fast as two on C3 exact (302 vs 304 ms), 3 % slower on C3 fast-math (290 vs 281 ms) and 17 % FASTER on C5
@@ -486,22 +455,7 @@ inline RenderVariant choose_variant(const RtSceneView& G, size_t smem_limit, boo
     RenderVariant v;
     v.sph       = (cull && G.n_groups > 0) ? RT_SPH_CULL : G.n_sph_pad >= kFilterFrom ? RT_SPH_FILTER : RT_SPH_DIRECT;
     v.tris      = G.n_tri_pad > 0;
-    v.parts     = 0u;
-    if (v.sph == RT_SPH_FILTER) {
-        // Lists + r*r is what several small CTAs per SM stage (their L1 serves the edge-stage records).  A block that
-        // leaves room for one CTA only owns all of shared memory: the edge-stage records and K go in as well — plane-stage
-        // survivors then read shared memory instead of L2 (C5: 80 % of all triangle pairs) — and r*r, which only the
-        // rare filter survivor reads, is the first part to stay in the blob.  RT_HOT_PARTS=<mask> overrides (A/B runs).
-        v.parts = RT_HOT_R2;
-        if (rt_hot_bytes(G, v.sph, RT_HOT_R2) > kLargeSmemFrom) {
-            static const uint32_t order[] = {RT_HOT_EDGE | RT_HOT_K | RT_HOT_R2, RT_HOT_EDGE | RT_HOT_K, RT_HOT_EDGE, RT_HOT_R2, 0u};
-            for (uint32_t parts : order)
-                if (rt_hot_bytes(G, v.sph, parts) <= smem_limit) { v.parts = parts; break; }
-        }
-        static const int forced = [] { const char* e = getenv("RT_HOT_PARTS"); return e && *e ? atoi(e) : -1; }();
-        if (forced >= 0) v.parts = (uint32_t)forced & (RT_HOT_EDGE | RT_HOT_K | RT_HOT_R2);
-    }
-    v.hot_bytes = rt_hot_bytes(G, v.sph, v.parts);
+    v.hot_bytes = rt_hot_bytes(G, v.sph);
     v.smem      = v.hot_bytes <= smem_limit;
     v.np        = v.sph == RT_SPH_FILTER ? filter_paths_per_lane() : 1;
     v.block     = (v.smem && v.hot_bytes > kLargeSmemFrom) ? (v.np == 2 ? kBlockLarge2 : kBlockLarge) : kBlockSmall;
@@ -550,9 +504,7 @@ cudaError_t launch_render(const RtFrameParams& P, const RtSceneView& G, int grid
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_limit);
             if (e != cudaSuccess) return e;
         }
-        RtSceneView Gk = G;
-        Gk.hot_parts   = v.parts;
-        k<<<grid, block, v.smem ? v.hot_bytes : 0, stream>>>(P, Gk);
+        k<<<grid, block, v.smem ? v.hot_bytes : 0, stream>>>(P, G);
         return cudaGetLastError();
     });
 }

@@ -138,8 +138,7 @@ RtSceneView World::Packed::view(const unsigned char* base) const
     v.cull_r2    = reinterpret_cast<const float*>(base + off_cull_r2);
     v.cull_orig  = reinterpret_cast<const uint32_t*>(base + off_cull_orig);
     v.n_groups   = n_groups;
-    v.tri_edge  = reinterpret_cast<const RtFloat4*>(base + off_tri_edge);
-    v.tri_k     = reinterpret_cast<const float*>(base + off_tri_k);
+    v.tri_cull  = reinterpret_cast<const RtFloat4*>(base + off_tri_cull);
     v.tri_v     = reinterpret_cast<const RtFloat4*>(base + off_tri_v);
     v.info      = reinterpret_cast<const RtPrimInfo*>(base + off_info);
     v.n_sph     = n_sph;
@@ -349,8 +348,7 @@ const World::Packed& World::packed() const
     const size_t off_plane_c = off; off += Tp * sizeof(RtFloat4);
     p->off_cull_r2    = off; off += align_up(8 * Gc * sizeof(float), 16);
     p->off_cull_orig  = off; off += align_up(8 * Gc * sizeof(uint32_t), 16);
-    p->off_tri_edge  = off; off += 4 * (Tp / 2) * sizeof(RtFloat4);
-    p->off_tri_k     = off; off += align_up(Tp * sizeof(float), 16);
+    p->off_tri_cull  = off; off += 5 * (Tp / 2) * sizeof(RtFloat4);
     p->off_tri_v     = off; off += 3 * T * sizeof(RtFloat4);
     off = align_up(off, 32);
     p->off_info      = off; off += P * sizeof(RtPrimInfo);
@@ -359,8 +357,7 @@ const World::Packed& World::packed() const
     auto* sph   = reinterpret_cast<RtFloat4*>(base + p->off_sph);
     auto* plane = reinterpret_cast<RtFloat4*>(base + p->off_tri_plane);
     auto* triv  = reinterpret_cast<RtFloat4*>(base + p->off_tri_v);
-    auto* edge  = reinterpret_cast<RtFloat4*>(base + p->off_tri_edge);
-    auto* trik  = reinterpret_cast<float*>(base + p->off_tri_k);
+    auto* cull  = reinterpret_cast<RtFloat4*>(base + p->off_tri_cull);
     auto* info  = reinterpret_cast<RtPrimInfo*>(base + p->off_info);
     for (size_t i = 0; i < S; ++i) {
         const Sphere& s = spheres[i];
@@ -419,13 +416,12 @@ const World::Packed& World::packed() const
         plane[j]     = {a.x, b.x, a.y, b.y};
         plane[j + 1] = {a.z, b.z, a.w, b.w};
         const RtFloat4 *ca = &cull_aos[3 * j], *cb = &cull_aos[3 * (j + 1)];
-        RtFloat4* q = &edge[4 * (j / 2)];
+        RtFloat4* q = &cull[5 * (j / 2)];
         q[0] = {ca[0].x, cb[0].x, ca[0].y, cb[0].y};
         q[1] = {ca[0].z, cb[0].z, ca[0].w, cb[0].w};
         q[2] = {ca[1].x, cb[1].x, ca[1].y, cb[1].y};
         q[3] = {ca[1].z, cb[1].z, ca[1].w, cb[1].w};
-        trik[j]     = ca[2].x;
-        trik[j + 1] = cb[2].x;
+        q[4] = {ca[2].x, cb[2].x, 0.f, 0.f};
     }
     std::memcpy(base + off_plane_b, plane, Tp * sizeof(RtFloat4));
     std::memcpy(base + off_plane_c, plane, Tp * sizeof(RtFloat4));

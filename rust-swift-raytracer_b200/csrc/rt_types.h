@@ -23,12 +23,9 @@
 //   [ cull_r2   : float  x 8Gc] r*r in the same order                                 warm
 //   [ cull_orig : u32    x 8Gc] list index of each sphere (hit-test order = tie-break order)  warm
 //   then
-//   [ tri_edge  : float4 x 2Tp]  per PAIR of triangles the approximate barycentric forms {G2.xyz, g2}, {G0.xyz, g0} of the
-//                               conservative edge-stage reject, as {G2x0,G2x1,G2y0,G2y1} {G2z0,G2z1,g2_0,g2_1}
-//                               {G0x0,G0x1,G0y0,G0y1} {G0z0,G0z1,g0_0,g0_1}          warm (plane-stage survivors)
-//   [ tri_k     : float  x Tp ]  the bound K of each triangle up to which that reject may be trusted      warm
-//                               (the FILTER kernels stage tri_edge / tri_k behind their lists when shared memory allows:
-//                                RT_HOT_* below)
+//   [ tri_cull  : float4 x 5Tp/2]  per PAIR of triangles {G2.xyz, g2}, {G0.xyz, g0}, K — approximate barycentric
+//                               gradients for the conservative edge-stage reject — as {G2x0,G2x1,G2y0,G2y1}
+//                               {G2z0,G2z1,g2_0,g2_1} {G0x0,..} {G0z0,..,g0_1} {K0,K1,0,0}   warm (plane-stage survivors)
 //   [ tri_v     : float4 x 3T]  {v_k.xyz, stored_normal[k]}       cool (reject survivors)
 //   [ info      : 32 B   x P ]  RtPrimInfo                        cold (one gather per hit), P = S+T
 //
@@ -97,8 +94,7 @@ struct RtSceneView {
     const RtFloat4*   cull_sph;   // [9*n_groups]   block C (followed by tri_plane again)
     const float*      cull_r2;    // [8*n_groups]
     const uint32_t*   cull_orig;  // [8*n_groups]
-    const RtFloat4*   tri_edge;   // [2*n_tri_pad]: 4 float4 per pair of triangles
-    const float*      tri_k;      // [n_tri_pad]
+    const RtFloat4*   tri_cull;   // [3T]
     const RtFloat4*   tri_v;      // [3T]
     const RtPrimInfo* info;       // [S+T]
     uint32_t          n_sph;
@@ -106,15 +102,7 @@ struct RtSceneView {
     uint32_t          n_tri;
     uint32_t          n_tri_pad;  // multiple of RT_TRI_GROUP
     uint32_t          n_groups;   // block C: groups of 8 spheres (0: the world has no block C)
-    uint32_t          hot_parts;  // RT_HOT_*: what the launch stages in shared memory behind the lists (set by the launcher)
-};
-
-// Optional parts of a FILTER kernel's shared-memory block, staged behind {sph_filter | tri_plane} in this order when
-// they fit (rt_kernels.cuh, choose_variant): what is not staged is read from the blob in global memory.
-enum : uint32_t {
-    RT_HOT_EDGE = 1u << 0,    // tri_edge: the edge-stage records (64 B per pair of triangles)
-    RT_HOT_K    = 1u << 1,    // tri_k
-    RT_HOT_R2   = 1u << 2,    // sph_r2: the exact r*r of filter survivors
+    uint32_t          pad;
 };
 
 // Row-tile sharding.  The frame's tiles (tile_rows image rows each, top to bottom) are dealt to

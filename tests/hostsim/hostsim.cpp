@@ -64,8 +64,8 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
                     if (live[p]) { d[p] = segment_begin<false>(L[p], P); o[p] = L[p].o; ++rays; }
                 }
                 if (!live[0] && !live[1]) break;
-                if (G.n_tri_pad) closest_hit_n<false, true, 2>(G.sph_filter, G.sph_r2, G.n_sph, G.n_sph_pad, G.tri_plane, G.tri_edge, G.tri_k, G.tri_v, G.n_tri_pad, o, d, P.one, h);
-                else             closest_hit_n<false, false, 2>(G.sph_filter, G.sph_r2, G.n_sph, G.n_sph_pad, G.tri_plane, G.tri_edge, G.tri_k, G.tri_v, G.n_tri_pad, o, d, P.one, h);
+                if (G.n_tri_pad) closest_hit_n<false, true, 2>(G.sph_filter, G.sph_r2, G.n_sph, G.n_sph_pad, G.tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, P.one, h);
+                else             closest_hit_n<false, false, 2>(G.sph_filter, G.sph_r2, G.n_sph, G.n_sph_pad, G.tri_plane, G.tri_cull, G.tri_v, G.n_tri_pad, o, d, P.one, h);
                 for (int p = 0; p < 2; ++p)
                     if (live[p]) segment_end<false, RT_SPH_FILTER, true>(L[p], G, G.sph_filter, d[p], h[p]);
             }
@@ -85,10 +85,10 @@ extern "C" int hostsim_render(const char* scene_text, const float cam12[12], uin
             // the kernel's loop for one lane; bit 31 of `flags` selects the FILTER variant, bit 30 the CULL variant
             while (trace && L.sample < spp) {
                 ++rays;
-                if (flags & 0x40000000u)      trace_segment<false, RT_SPH_CULL, true>(L, P, G, G.sph_filter, G.sph_r2, cv, G.tri_plane, G.tri_edge, G.tri_k);
-                else if (flags & 0x80000000u) trace_segment<false, RT_SPH_FILTER, true>(L, P, G, G.sph_filter, G.sph_r2, cv, G.tri_plane, G.tri_edge, G.tri_k);
-                else if (G.n_tri_pad)         trace_segment<false, RT_SPH_DIRECT, true>(L, P, G, G.sph, nullptr, cv, G.tri_plane, G.tri_edge, G.tri_k);
-                else                          trace_segment<false, RT_SPH_DIRECT, false>(L, P, G, G.sph, nullptr, cv, G.tri_plane, G.tri_edge, G.tri_k);
+                if (flags & 0x40000000u)      trace_segment<false, RT_SPH_CULL, true>(L, P, G, G.sph_filter, G.sph_r2, cv, G.tri_plane);
+                else if (flags & 0x80000000u) trace_segment<false, RT_SPH_FILTER, true>(L, P, G, G.sph_filter, G.sph_r2, cv, G.tri_plane);
+                else if (G.n_tri_pad)         trace_segment<false, RT_SPH_DIRECT, true>(L, P, G, G.sph, nullptr, cv, G.tri_plane);
+                else                          trace_segment<false, RT_SPH_DIRECT, false>(L, P, G, G.sph, nullptr, cv, G.tri_plane);
             }
             out32[L.out_index] = resolve_pixel<false>(L.acc_r, L.acc_g, L.acc_b, pixel_alpha(1.0f, spp > 0 ? spp : 0),
                                                       P.resolve_spp);
