@@ -568,6 +568,8 @@ def main():
                                       "(fused into the render kernels: every finished pixel is stored into rank 0's frame over NVLink, CUDA IPC)"
                                       if gather == "peer" else "(compact buffers + dist.gather)"))
                    if n_gpus > 1 else "1 GPU",
+                   "launch": {"block": int(st0.block), "grid": int(st0.grid), "smem_bytes": int(st0.smem_bytes),
+                              "sample_items": bool(st0.sample_items), "paths_per_lane": int(st0.paths_per_lane)},
                    "stolen_slots_first_step": int(stolen_first) if n_gpus > 1 else 0,
                    "l2": "flushed between steps (256 MiB write, outside the CUDA events)",
                    "wall_ms_per_step_incl_flush": t_wall / args.steps * 1e3,
