@@ -84,8 +84,17 @@ __global__ void rt_selftest_sqrt_kernel(unsigned long long* mismatches)
         const float x = __uint_as_float((uint32_t)b);
         const bool  in = sqrt_in_range(x);
         bad += in != (x >= RT_SQRT_LO && x <= RT_SQRT_HI);
-        if (in) bad += !same_bits(sqrt_ranged(x), sqrtf(x));
         const float nx = __uint_as_float((uint32_t)b | 0x80000000u);      // negatives never pass
+        if (in) {
+            bad += !same_bits(sqrt_ranged(x), sqrtf(x));
+            // the sphere roots' two-wide form on the negated operand: -sqrt(x) in BOTH lanes (the other lane holds a
+            // second in-range value, so that the lanes cannot share a result by accident)
+            const float x2 = __uint_as_float(0x0d800000u + ((uint32_t)b * 2654435761u) % 0x64000001u);
+            float s0, s1;
+            f2_split(neg_sqrt_pair(f2_make(nx, -x2)), s0, s1);
+            bad += !same_bits(s0, -sqrtf(x));
+            bad += !same_bits(s1, -sqrtf(x2));
+        }
         bad += sqrt_in_range(nx);
     }
     if (bad) atomicAdd(mismatches, bad);
