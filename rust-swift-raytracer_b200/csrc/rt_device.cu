@@ -288,6 +288,8 @@ ShardLaunch enqueue_shard(DeviceContext& ctx, const DeviceScene& scene, const Ca
               (opt.accum_out ? RT_FLAG_ACCUM_OUT : 0u) | (opt.no_resolve ? RT_FLAG_NO_RESOLVE : 0u) |
               (L.compact ? RT_FLAG_COMPACT_OUT : 0u) | (opt.group_cull ? RT_FLAG_GROUP_CULL : 0u);
     P.tile_rows    = opt.tile_rows;
+    P.div_subtiles_x       = rt_divisor((W + 7u) >> 3);
+    P.div_chunks_per_strip = rt_divisor(((W + 7u) >> 3) * (opt.tile_rows >> 2));
     P.tile_first   = opt.shard_index;
     P.tile_stride  = opt.shard_count;
     P.n_tiles      = L.n_tiles;

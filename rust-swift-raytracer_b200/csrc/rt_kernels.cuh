@@ -115,11 +115,11 @@ __device__ __forceinline__ PixelSlot decode_slot(const RtFrameParams& P, uint32_
         sample_of_item   = chunk - c * (uint32_t)P.spp;
         chunk            = c;
     }
-    const uint32_t rs    = chunk / chunks_per_strip;
+    const uint32_t rs    = rt_div(chunk, P.div_chunks_per_strip);
     const uint32_t strip = q_tiles - 1u - rs;
     const uint32_t rc    = chunk - rs * chunks_per_strip;
     const uint32_t c     = chunks_per_strip - 1u - rc;
-    const uint32_t sy    = c / subtiles_x;
+    const uint32_t sy    = rt_div(c, P.div_subtiles_x);
     const uint32_t sx    = c - sy * subtiles_x;
     const uint32_t x     = sx * 8u + (in & 7u);
     const uint32_t yin   = sy * 4u + (in >> 3);
@@ -237,7 +237,7 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
     uint32_t segments = 0;
     for (;;) {
         // ---- 1. paths without a pixel take the next slots of the warp's slab ----
-        bool any_have = false;
+        uint32_t lacking = FULL;                  // lanes none of whose paths has a pixel
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             Lane&    Lp   = L[p];
@@ -282,9 +282,9 @@ rt_render_kernel(const __grid_constant__ RtFrameParams P, const __grid_constant_
                 pool_next += min(avail, (uint32_t)__popc(need));
                 need = __ballot_sync(FULL, !Lp.have);
             }
-            any_have = any_have || Lp.have;
+            lacking &= need;                      // `need` is the ballot of !have as it stands after the refill
         }
-        if (__ballot_sync(FULL, any_have) == 0u) break;
+        if (lacking == FULL) break;               // no pixel anywhere in the warp and every queue is empty
 
         // ---- 1b. fused passes: a pixel's pass p continues the sums its pass p-1 stored; the alpha sum
         //          (1 + samples so far, pixel_alpha) tags the record.  Not there yet: look again next time

@@ -132,6 +132,39 @@ enum : uint32_t {
     RT_FLAG_RESOLVE_EACH_PASS = 1u << 7,   // fused progressive passes: store the resolved pixel after every pass
 };
 
+// Division of a 32-bit unsigned by a launch constant without the divide (Granlund & Montgomery's round-up form:
+// exact for EVERY n < 2^32 and every d in [1, 2^31]): with l = ceil(log2 d), mul = floor(2^32 (2^l - d) / d) + 1,
+//     t = hi32(mul * n),  n / d = (t + ((n - t) >> min(l, 1))) >> max(l - 1, 0).
+// Five integer instructions where the compiler's own expansion of `n / d` (float reciprocal, two corrections) takes ~20;
+// the slot decode of the render kernel divides twice per pixel (rt_kernels.cuh, decode_slot).
+struct RtDivisor { uint32_t d, mul, sh1, sh2; };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline RtDivisor rt_divisor(uint32_t d)
+{
+    RtDivisor k;
+    k.d = d;
+    uint32_t l = 0;
+    while (l < 32u && (1ull << l) < d) ++l;                              // ceil(log2 d); d = 0 is never divided by
+    k.mul = (uint32_t)((((1ull << l) - d) << 32) / (d ? d : 1u)) + 1u;
+    k.sh1 = l < 1u ? l : 1u;
+    k.sh2 = l > 0u ? l - 1u : 0u;
+    return k;
+}
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t rt_div(uint32_t n, const RtDivisor& k)
+{
+#if defined(__CUDA_ARCH__)
+    const uint32_t t = __umulhi(k.mul, n);
+#else
+    const uint32_t t = (uint32_t)(((unsigned long long)k.mul * n) >> 32);
+#endif
+    return (t + ((n - t) >> k.sh1)) >> k.sh2;
+}
+
 // One work queue of a launch.  Queue 0 is the launch's own shard; further entries are the shards
 // of OTHER GPUs rendering the same frame, whose work counter (and float4 sums) live in their
 // memory and are reached through peer / CUDA-IPC mappings: when a warp finds its own queue empty
@@ -185,6 +218,9 @@ struct RtFrameParams {
     unsigned int* tile_flags;
     uint32_t  tile_epoch;
     uint32_t  pad_tile;
+    // divisors of the slot decode (set by the host next to width / tile_rows): sub-tiles of 8x4 pixels per strip of
+    // tile_rows rows, and per row of sub-tiles
+    RtDivisor div_chunks_per_strip, div_subtiles_x;
     uint32_t  n_queues;      // >= 1
     RtQueue   queues[RT_MAX_QUEUES];   // [0] = the launch's own shard (work_counter / accum above), then the peers
 };

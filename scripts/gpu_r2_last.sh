@@ -1,6 +1,7 @@
 #!/bin/bash
 # Last evidence call of round 2: GPU suite + smoke on the current library, same-box A/B of the small-scene kernel
-# against the library before the pair-wise root finding (lib_base), and the default bench line of both.
+# against the previous commit's library (lib_base), and the default bench line.  RT_LAST_BASE_LINE=1 also takes the
+# default line of lib_base.
 set -u
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
@@ -19,7 +20,9 @@ for rep in 1 2; do
   timeout 120 python bench.py --workload c2 --steps 40 $B 2>>gpurun_out/bench.err | line "[new ]"
 done
 timeout 200 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "bench rc=$?"
-RT_LIB_VARIANT=base timeout 200 python bench.py > gpurun_out/bench_default_base.json 2>> gpurun_out/bench_default.err; echo "bench(base) rc=$?"
+if [ "${RT_LAST_BASE_LINE:-0}" = 1 ]; then
+  RT_LIB_VARIANT=base timeout 200 python bench.py > gpurun_out/bench_default_base.json 2>> gpurun_out/bench_default.err; echo "bench(base) rc=$?"
+fi
 python - <<'PY'
 import json
 for f in ("bench_default.json", "bench_default_base.json"):

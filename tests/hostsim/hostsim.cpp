@@ -150,3 +150,31 @@ extern "C" int hostsim_check_cull(const char* scene_text, uint32_t* n_groups_out
     if (n_always_out) *n_always_out = always;
     return 0;
 }
+
+// rt_types.h rt_divisor / rt_div against the plain `/`: every divisor of `dlist` (plus the powers of two and their
+// neighbours) with numerators around every multiple boundary it can reach, the extremes, and `n_random` random
+// numerators each.  Returns the number of mismatches.
+extern "C" uint64_t hostsim_divisor_mismatches(const uint32_t* dlist, uint32_t n_d, uint32_t n_random, uint32_t seed)
+{
+    std::vector<uint32_t> ds(dlist, dlist + n_d);
+    for (uint32_t l = 0; l <= 31u; ++l)
+        for (int64_t delta = -1; delta <= 1; ++delta) {
+            const int64_t d = ((int64_t)1 << l) + delta;
+            if (d >= 1 && d <= ((int64_t)1 << 31)) ds.push_back((uint32_t)d);
+        }
+    uint64_t bad = 0;
+    uint32_t x = seed ? seed : 1u;
+    auto next = [&x] { x ^= x << 13; x ^= x >> 17; x ^= x << 5; return x; };
+    for (uint32_t d : ds) {
+        const RtDivisor k = rt_divisor(d);
+        auto check = [&](uint32_t n) { bad += rt_div(n, k) != n / d; };
+        for (uint32_t n : {0u, 1u, d - 1u, d, d + 1u, 0x7fffffffu, 0x80000000u, 0xfffffffeu, 0xffffffffu}) check(n);
+        for (uint32_t i = 0; i < n_random; ++i) {
+            const uint32_t n = next();
+            check(n);
+            const uint32_t m = n / d * d;                  // a multiple of d and its neighbours
+            check(m); check(m - 1u); check(m + (d - 1u));
+        }
+    }
+    return bad;
+}

@@ -19,6 +19,8 @@ def _load(name):
     L.hostsim_render.restype = C.c_int
     L.hostsim_render.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.c_int32, C.c_int32,
                                  C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.hostsim_divisor_mismatches.restype = C.c_uint64
+    L.hostsim_divisor_mismatches.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint32]
     L.hostsim_check_cull.restype = C.c_int
     L.hostsim_check_cull.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     return L
@@ -168,3 +170,16 @@ def test_c5_triangles_with_perturbed_reciprocals(hostsim_perturbed, ob, scenes):
     rc = hostsim_perturbed.hostsim_render(text.encode(), cf.ctypes.data_as(C.POINTER(C.c_float)), W, H, spp, depth,
                                           ob.SEED_DEFAULT, 0x80000000, 0, 0, out.ctypes.data, C.byref(n))
     assert rc == 0 and n.value == rays and np.array_equal(out, want)
+
+
+def test_constant_divisors_of_the_slot_decode_equal_the_divide(hostsim):
+    """rt_types.h rt_divisor / rt_div (the render kernel's slot decode divides by two launch constants): equal to `/` for
+    every sub-tile count a frame of up to 65,536 x 65,536 pixels and any tile height can produce (a sample of them), all
+    powers of two and their neighbours, numerators at every boundary and 20,000 random ones each."""
+    import numpy as np
+    widths = list(range(1, 700)) + [1920, 3840, 4096, 7680, 8192, 16384, 65535, 65536]
+    ds = sorted({(w + 7) // 8 for w in widths} | {((w + 7) // 8) * r for w in widths for r in (1, 4, 16, 64, 4096)}
+                | {3, 7, 641, 6700417, 2**31 - 1, 2**31})
+    ds = [d for d in ds if 1 <= d <= 2**31]
+    arr = (C.c_uint32 * len(ds))(*ds)
+    assert hostsim.hostsim_divisor_mismatches(arr, len(ds), 20000, 12345) == 0
