@@ -450,8 +450,8 @@ def main():
             e2e = {"value": rays_frame / t / 1e6, "unit": "Mrays/s", "ms_per_frame": t * 1e3,
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": W * H * 4,
                    "api": "render_with_options (C ABI), PAGEABLE host framebuffer (np.zeros / malloc): the kernel stores "
-                          "its pixels into the library's pinned staging frame over PCIe while it renders, then one memcpy "
-                          "into the caller's buffer"}
+                          "its pixels into the library's pinned staging frame over PCIe and flags every finished 16-row tile; "
+                          "the calling thread copies flagged tiles into the caller's buffer while the kernel renders the rest"}
             t = time_calls(lambda: rt.render_with_options(fb_pin, handle, opts), args.steps)
             e2e_pinned = {"value": rays_frame / t / 1e6, "unit": "Mrays/s", "ms_per_frame": t * 1e3,
                           "api": "render_with_options (C ABI), pinned framebuffer from rt_alloc_pixels: pixels stored straight "
