@@ -183,3 +183,48 @@ def test_constant_divisors_of_the_slot_decode_equal_the_divide(hostsim):
     ds = [d for d in ds if 1 <= d <= 2**31]
     arr = (C.c_uint32 * len(ds))(*ds)
     assert hostsim.hostsim_divisor_mismatches(arr, len(ds), 20000, 12345) == 0
+
+
+def _extreme_discriminant_world(variant: int) -> str:
+    """Sphere groups whose discriminants leave [2^-100, 2^100] — the range the bare square-root sequences of
+    sphere_group are used on: radii of 1e16..1e18 (disc ~ 1e32..1e36), radii whose square is denormal or zero in f32
+    (disc a rounding residue: tiny, zero or negative), next to ordinary spheres of the same group, some of them
+    concentric / coincident so that equal roots meet the reference's list-order tie rule."""
+    big = ["10000000000000000.0", "300000000000000000.0", "1000000000000000000.0"][variant % 3]
+    tiny = ["0.00000000000000000001", "0.000000000000000000000001", "0.0000000000000000000000000001"][variant % 3]
+    lines = ["camera origin 0.0 0.25 1.0 aspect 1.5;",
+             "material G : Diffuse color 0.5 0.6 0.4;", "material M : Metal color 0.8 0.8 0.9 fuzz 0.1;",
+             "material D : Dielectric ir 1.5;", "material R : Diffuse color 0.9 0.2 0.2;"]
+    def sphere(x, y, z, r, m): lines.append(f"sphere center {x} {y} {z} radius {r} material {m};")
+    sphere("0.0", "-" + big, "-1.0", big, "G")                 # a "ground" whose discriminant overflows the range
+    sphere("0.0", "0.3", "-2.0", "0.5", "R")
+    sphere("0.0", "0.25", "-1.5", tiny, "M")                  # r*r underflows: disc is a rounding residue
+    sphere("1.0", "0.3", "-2.5", "0.5", "M")
+    sphere("1.0", "0.3", "-2.5", "0.5", "D")                  # coincident with the previous one: equal roots, first wins
+    sphere("-1.2", "0.4", "-2.2", "0.6", "D")
+    sphere("-1.2", "0.4", "-2.2", "0.3", "R")                 # concentric, inside a dielectric
+    sphere("0.0", big, "-1.0", big, "G")                       # a "ceiling" of the same size: two huge discs in one group
+    if variant >= 3:                                           # a second group: ordinary spheres + one more tiny one
+        for i in range(7):
+            sphere(f"{-2.0 + 0.6 * i:.1f}", "0.1", "-3.5", "0.25", "RMD"[i % 3])
+        sphere("0.5", "0.25", "-1.2", tiny, "R")
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("variant", range(6))
+def test_sphere_groups_with_out_of_range_discriminants(hostsim, ob, variant):
+    """rt_trace.cuh sphere_group: the pair-wise root finding serves groups whose discriminants all lie in the proven range;
+    any other group takes the per-sphere path and its sqrtf tail with the tie rule spelled out.  Both must give the
+    oracle's frame and ray count on groups that mix ordinary, overflowing and vanishing discriminants."""
+    text = _extreme_discriminant_world(variant)
+    cam, world = ob.parse_input(text)
+    W, H, spp, depth = 48, 32, 3, 8
+    want, rays, _ = ob.ray_trace(world, cam, W, H, spp, depth)
+    assert rays > W * H * spp                                   # something is hit and bounces
+    cf = cam.floats()
+    out = np.zeros((H, W, 4), np.uint8)
+    n = C.c_uint64()
+    rc = hostsim.hostsim_render(text.encode(), cf.ctypes.data_as(C.POINTER(C.c_float)), W, H, spp, depth,
+                                ob.SEED_DEFAULT, 0, 0, 0, out.ctypes.data, C.byref(n))
+    assert rc == 0 and n.value == rays
+    assert np.array_equal(out, want)
