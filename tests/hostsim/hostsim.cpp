@@ -178,3 +178,58 @@ extern "C" uint64_t hostsim_divisor_mismatches(const uint32_t* dlist, uint32_t n
     }
     return bad;
 }
+
+// The render kernel's work space (rt_trace.cuh decode_slot): for one launch geometry, decode EVERY slot of every shard
+// exactly as the kernel does and check that the valid slots are a bijection onto (pixel, pass[, sample]) of the frame,
+// that every shard only touches its own tiles (rt_shard_tile), and that out_index addresses the frame (or the shard's
+// compact buffer).  Returns the number of violations.  items != 0: RT_FLAG_SAMPLE_ITEMS with spp samples.
+extern "C" uint64_t hostsim_decode_violations(uint32_t W, uint32_t H, uint32_t tile_rows, uint32_t shard_count,
+                                              uint32_t passes, int32_t spp, int items, int compact)
+{
+    using namespace rt;
+    const uint32_t subtiles_x = (W + 7u) >> 3, chunks_per_strip = subtiles_x * (tile_rows >> 2);
+    const uint32_t per_slot   = items ? (uint32_t)spp : 1u;
+    const uint32_t slots_per_tile = chunks_per_strip * 32u * per_slot;
+    std::vector<uint32_t> seen((size_t)W * H * passes * per_slot, 0u);
+    uint64_t bad = 0;
+    for (uint32_t shard = 0; shard < shard_count; ++shard) {
+        RtFrameParams P{};
+        P.width = W; P.height = H; P.spp = spp; P.passes = passes; P.tile_rows = tile_rows;
+        P.tile_first = shard; P.tile_stride = shard_count;
+        P.flags = (items ? RT_FLAG_SAMPLE_ITEMS : 0u) | (compact ? RT_FLAG_COMPACT_OUT : 0u);
+        P.div_subtiles_x       = rt_divisor(subtiles_x);
+        P.div_chunks_per_strip = rt_divisor(chunks_per_strip);
+        const uint32_t q_tiles = shard_tile_count(H, tile_rows, shard, shard_count);
+        const uint32_t slots_per_pass = q_tiles * slots_per_tile;
+        std::vector<uint32_t> compact_seen(compact ? (size_t)q_tiles * tile_rows * W : 0, 0u);
+        for (uint32_t slot = 0; slot < slots_per_pass * passes; ++slot) {
+            uint32_t sample = 0, pass = 0;
+            const PixelSlot s = decode_slot(P, slot, subtiles_x, chunks_per_strip, shard, q_tiles, slots_per_pass, sample, pass);
+            if (!s.valid) continue;
+            if (s.column >= W || s.image_row >= H || pass >= passes || sample >= per_slot) { ++bad; continue; }
+            const uint32_t tile = s.image_row / tile_rows;
+            bool mine = false;
+            for (uint32_t j = 0; j < q_tiles; ++j) mine = mine || rt_shard_tile(shard, shard_count, j) == tile;
+            bad += !mine;
+            if (compact) {
+                if (s.out_index >= compact_seen.size()) { ++bad; continue; }
+                if (pass == 0 && sample == 0) ++compact_seen[s.out_index];
+            } else {
+                bad += s.out_index != s.image_row * W + s.column;
+            }
+            ++seen[(((size_t)pass * per_slot + sample) * H + s.image_row) * W + s.column];
+        }
+        uint64_t used = 0;
+        for (uint32_t c : compact_seen) { bad += c > 1u; used += c; }
+        if (compact) {                                           // every pixel of the shard's tiles, once
+            uint64_t rows = 0;
+            for (uint32_t j = 0; j < q_tiles; ++j) {
+                const uint32_t first = rt_shard_tile(shard, shard_count, j) * tile_rows;
+                rows += first < H ? (H - first < tile_rows ? H - first : tile_rows) : 0u;
+            }
+            bad += used != rows * W;
+        }
+    }
+    for (uint32_t c : seen) bad += c != 1u;                      // every (pixel, pass, sample) exactly once over all shards
+    return bad;
+}

@@ -21,6 +21,8 @@ def _load(name):
                                  C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_uint64)]
     L.hostsim_divisor_mismatches.restype = C.c_uint64
     L.hostsim_divisor_mismatches.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_uint32]
+    L.hostsim_decode_violations.restype = C.c_uint64
+    L.hostsim_decode_violations.argtypes = [C.c_uint32] * 5 + [C.c_int32, C.c_int, C.c_int]
     L.hostsim_check_cull.restype = C.c_int
     L.hostsim_check_cull.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     return L
@@ -228,3 +230,21 @@ def test_sphere_groups_with_out_of_range_discriminants(hostsim, ob, variant):
                                 ob.SEED_DEFAULT, 0, 0, 0, out.ctypes.data, C.byref(n))
     assert rc == 0 and n.value == rays
     assert np.array_equal(out, want)
+
+
+def test_work_space_decode_is_a_bijection_onto_the_frame(hostsim):
+    """rt_trace.cuh decode_slot (8x4 sub-tiles, bottom-up strips, boustrophedon tile deal, pass-major fused passes, sample
+    items, compact shard buffers, the constant-divisor arithmetic): over all shards every (pixel, pass, sample) is produced
+    exactly once, by the shard that owns its tile, with the right output index — for ragged widths and heights, every
+    tile height up to 64, 1-8 shards."""
+    import itertools
+    sizes = [(1, 1), (7, 5), (8, 4), (9, 17), (33, 31), (64, 64), (100, 37), (257, 66), (401, 225), (1921, 130)]
+    n = 0
+    for (W, H), tile_rows, shards in itertools.product(sizes, (4, 8, 16, 20, 64), (1, 2, 3, 8)):
+        for passes, spp, items, compact in ((1, 1, 0, 0), (3, 2, 0, 0), (1, 3, 1, 0), (1, 1, 0, 1), (2, 1, 0, 1)):
+            if W * H * passes * max(spp if items else 1, 1) > 600_000:
+                continue
+            assert hostsim.hostsim_decode_violations(W, H, tile_rows, shards, passes, spp, items, compact) == 0, \
+                (W, H, tile_rows, shards, passes, spp, items, compact)
+            n += 1
+    assert n > 500
