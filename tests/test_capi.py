@@ -171,3 +171,36 @@ def test_write_image_equals_the_oracle_writer_byte_for_byte(rt, ob, tmp_path):
         raw = (tmp_path / "got6.ppm").read_bytes()
         head = b"P6\n%d %d\n255\n" % (W, H)
         assert raw.startswith(head) and raw[len(head):] == fb.pixels[:, :, :3].tobytes()
+
+
+def test_invalid_options_fail_before_any_device_work_and_leave_the_frame_alone(rt, scenes):
+    """Errors never cross the ABI: a bad option block makes render_with_options fail with a text in
+    rt_last_error() — decided on the host, so this holds on a box without a GPU — and the caller's pixels are untouched."""
+    import numpy as np
+    h = rt.load_world(scenes.default_world())
+    fb = rt.Framebuffer(24, 16)
+    fb.pixels[...] = 0xA5
+    cases_ = [
+        (dict(tile_rows=6), "tile_rows"), (dict(tile_rows=2), "tile_rows"),       # (0 means the default, 16)
+        (dict(shard_index=2, shard_count=2), "shard"),
+        (dict(passes=3), "multiple of passes"),
+        (dict(accum_in=True), "accum"),
+        (dict(peer_queues=[(4096, i) for i in range(9)], shard_count=9, full_frame_out=True), "too many peer queues"),
+        (dict(peer_queues=[(4096, 0), (8192, 1)], shard_count=3, full_frame_out=True), "every shard"),
+        (dict(peer_queues=[(4096, 0), (8192, 1)], shard_count=2), "full-frame"),
+    ]
+    for kw, needle in cases_:
+        with pytest.raises(rt.RenderError) as e:
+            rt.render_with_options(fb, h, rt.Options(4, 4, **kw))
+        assert needle in str(e.value), (kw, str(e.value))
+        assert needle in rt.last_error()
+        assert np.all(fb.pixels == 0xA5), kw
+
+
+def test_load_world_reports_the_parse_error_instead_of_panicking(rt):
+    """lib.rs:37-46 unwraps the parse result (a panic across the FFI); here load_world returns NULL and
+    rt_last_error() names the reference's error class."""
+    for text in ("sphere center 0 0 0 radius 1 material nope;", "camera origin 0 0;", "material M : Shiny;", "\xff"):
+        with pytest.raises(rt.ParseError) as e:
+            rt.load_world(text)
+        assert "ParseError" in str(e.value) and rt.last_error() == str(e.value)
