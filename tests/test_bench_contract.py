@@ -30,10 +30,7 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
-def test_gpu_arm_fails_loudly_without_a_device():
-    import importlib
-    sys.path.insert(0, str(ROOT))
-    rt = importlib.import_module("rust-swift-raytracer_b200")
+def test_gpu_arm_fails_loudly_without_a_device(rt):          # `rt` builds the library in a fresh checkout
     if rt.device_count() > 0:
         import pytest
         pytest.skip("a CUDA device is present")
